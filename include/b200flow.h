@@ -1,0 +1,157 @@
+/* b200flow.h -- C ABI of libb200flow.so: the B200-native (sm_100a) coarse-to-fine HS / BA / Classic+NL
+ * optical-flow hot path.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * The reference (jordanshivers/optical-flow-python) is pure Python and has no FFI of its own: its
+ * extension surface is its Python API.  Each entry point below replaces one Python-level seam of the
+ * reference (cited as file:line relative to the reference root) and is what a ctypes binding inside
+ * that package would call -- see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - all arrays are C-contiguous float64 unless stated; images are (H,W,C) interleaved exactly as the
+ *     NumPy arrays of the reference are; flow is (H,W,2) interleaved (u,v).
+ *   - functions without a `_dev` suffix take HOST pointers and do their own H2D / D2H copies on the
+ *     context's stream; `_dev` functions take DEVICE pointers on the context's device.
+ *   - every function returns 0 on success or a negative status:
+ *        B200FLOW_EINVAL (-1) bad argument      -> Python shim raises ValueError
+ *        B200FLOW_ECUDA  (-2) CUDA runtime error -> RuntimeError
+ *        B200FLOW_ENOCONV(-3) solver hit maxit before reaching tol (result still written)
+ *     and b200flow_last_error(ctx) describes the last failure.
+ *   - a context owns one CUDA stream and a device arena; it is not thread-safe, distinct contexts are.
+ *   - there is NO CPU fallback: b200flow_ctx_create fails with B200FLOW_ECUDA when no sm_100 GPU is usable.
+ */
+#ifndef B200FLOW_H
+#define B200FLOW_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FLOW_EINVAL  (-1)
+#define B200FLOW_ECUDA   (-2)
+#define B200FLOW_ENOCONV (-3)
+
+#define B200FLOW_ABI_VERSION 1
+
+typedef struct b200flow_ctx b200flow_ctx;
+
+/* robust penalty; kind = index into PENALTY_MAP order (optical_flow/robust/robust_function.py:16-27):
+ * 0 quadratic, 1 lorentzian, 2 charbonnier, 3 generalized_charbonnier, 4 geman_mcclure, 5 huber,
+ * 6 tukey, 7 gaussian, 8 tdist, 9 tdist_unnorm.  p0,p1 = RobustFunction.sigma[0..1]. */
+typedef struct { int kind; double p0, p1; } b200flow_penalty;
+
+enum { B200FLOW_HS = 0, B200FLOW_BA = 1, B200FLOW_CLASSICNL = 2 };
+enum { B200FLOW_INTERP_BICUBIC = 0, B200FLOW_INTERP_CUBIC = 1, B200FLOW_INTERP_BILINEAR = 2 };
+enum { B200FLOW_SOLVER_EXACT = 0,   /* replaces 'backslash' (spsolve): block-Jacobi PCG run to `tol` */
+       B200FLOW_SOLVER_PCG = 1 };   /* the reference's own approximate 'pcg' mode (Jacobi, rtol/maxiter as given) */
+
+/* Mirrors the public attributes of HSOpticalFlow / BAOpticalFlow / ClassicNLOpticalFlow
+ * (methods/base.py:21-63, hs.py:23-47, ba.py:26-55, classic_nl.py:32-87; presets methods/config.py:10-176). */
+typedef struct {
+  int method;                 /* B200FLOW_HS | _BA | _CLASSICNL */
+  int interp;                 /* interpolation_method */
+  int texture;                /* 1: ROF structure-texture decomposition, 0: scale_image(0,255), -1: none (compute_flow_base) */
+  int gnc_iters, max_iters, max_linear, max_warping_iters, limit_update;
+  int pyramid_levels;         /* used only when auto_level == 0 (BA / Classic+NL) */
+  int auto_level;
+  int gnc_pyramid_levels;
+  double pyramid_spacing, gnc_pyramid_spacing;
+  double lambda, lambda_q, alpha0, alp, blend;
+  double deriv_filter[5];
+  double sigmaD2, sigmaS2;    /* HS only */
+  b200flow_penalty rho_su[2], rho_sv[2], rho_d;   /* robust penalties */
+  b200flow_penalty qua_su[2], qua_sv[2], qua_d;   /* their quadratic GNC stand-ins (ba.py:150-160, classic_nl.py:212-226) */
+  int median_h, median_w;     /* median_filter_size; 0 = None */
+  int mf_iter;                /* HS */
+  int area_hsz;               /* Classic+NL weighted-median half window */
+  double sigma_i;             /* Classic+NL colour sigma */
+  double occ_sigma_d, occ_sigma_i;  /* detect_occlusion defaults 0.3, 20 (utils/occlusion.py:6) */
+  int solver;                 /* B200FLOW_SOLVER_* */
+  double tol;                 /* relative residual ||r||/||b|| target */
+  int maxit;
+  int rof_iters;              /* 100 */
+  double rof_theta;           /* 1/8 */
+  int final_median;           /* HS: median once more after the finest level (hs.py:95-97) */
+} b200flow_params;
+
+/* per-call statistics of b200flow_estimate*, optional (may be NULL) */
+typedef struct {
+  int solves;                 /* linear solves performed (per batch, not per pair) */
+  long long pcg_iters;        /* sum over solves of the max iteration count over the batch */
+  long long pcg_pixel_iters;  /* sum over solves and pairs of iterations x level pixels */
+  int kernel_launches;        /* CUDA kernels launched by this call */
+  int not_converged;          /* solves that stopped at maxit */
+  double solver_ms, warp_ms, filter_ms, pre_ms, total_ms;  /* CUDA-event times on the ctx stream (0 unless timing enabled) */
+} b200flow_stats;
+
+int  b200flow_abi_version(void);
+int  b200flow_ctx_create(int device, b200flow_ctx **out);
+void b200flow_ctx_destroy(b200flow_ctx *ctx);
+const char *b200flow_last_error(const b200flow_ctx *ctx);   /* ctx may be NULL: last creation error */
+int  b200flow_ctx_set_timing(b200flow_ctx *ctx, int enabled);   /* per-stage CUDA-event timing into b200flow_stats */
+int  b200flow_ctx_sync(b200flow_ctx *ctx);
+void *b200flow_ctx_stream(b200flow_ctx *ctx);               /* the cudaStream_t, for torch / event interop */
+int  b200flow_ctx_num_sms(const b200flow_ctx *ctx);
+
+/* ---- whole pipeline: replaces {HS,BA,ClassicNL}OpticalFlow.compute_flow (hs.py:49-99, ba.py:57-138,
+ *      classic_nl.py:89-198) for a batch of B same-size pairs.
+ *      images (B,H,W,2) gray frame1/frame2; color (B,H,W,C) or NULL (C in {0,1,3}); init (B,H,W,2) or NULL;
+ *      uv_out (B,H,W,2). */
+int b200flow_estimate(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C,
+                      const double *images, const double *color, const double *init, double *uv_out,
+                      b200flow_stats *stats);
+int b200flow_estimate_dev(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C,
+                          const double *images_dev, const double *color_dev, const double *init_dev,
+                          double *uv_out_dev, b200flow_stats *stats);
+/* ---- replaces estimate_flow's colour preprocessing + compute_flow (interface.py:11-71): rgb (B,H,W,3)
+ *      uint8 frames; gray = _rgb2gray (interface.py:74-88), Lab = _rgb2lab + per-channel scale (91-141, 55-64) */
+int b200flow_estimate_rgb8(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W,
+                           const unsigned char *rgb1, const unsigned char *rgb2, int use_color,
+                           double *uv_out, b200flow_stats *stats);
+int b200flow_estimate_rgb8_dev(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W,
+                               const unsigned char *rgb1_dev, const unsigned char *rgb2_dev, int use_color,
+                               double *uv_out_dev, b200flow_stats *stats);
+
+/* ---- stage-level entry points, one per L1 seam of the reference (host pointers) ---- */
+/* interface.py:74-88 / 91-141: rgb (H,W,3) float64 -> gray (H,W) ; lab (H,W,3), optionally each channel scaled to [0,255] */
+int b200flow_rgb2gray(b200flow_ctx*, const double *rgb, int H, int W, double *gray);
+int b200flow_rgb2lab(b200flow_ctx*, const double *rgb, int H, int W, int scale_channels, double *lab);
+/* utils/image_processing.py:6-26 */
+int b200flow_scale_image(b200flow_ctx*, const double *in, long long n, double lo, double hi, double *out);
+/* utils/image_processing.py:52-136 */
+int b200flow_rof_texture(b200flow_ctx*, const double *img, int H, int W, int C, double theta, int iters,
+                         double alp, double *out);
+/* utils/pyramid.py:44-73 compute_image_pyramid(img, f, n_levels, ratio): f is an odd square (fs x fs, fs <= 9)
+ * correlation kernel (methods/base.py:174-190 builds it with fspecial_gaussian), ratio < 1 the downsampling ratio.
+ * Hs/Ws (levels ints) are always written; outs may be NULL to query sizes only, else outs[l] (may itself be NULL)
+ * receives level l as (Hs[l],Ws[l],C). */
+int b200flow_pyramid(b200flow_ctx*, const double *img, int H, int W, int C, int levels, const double *f, int fs,
+                     double ratio, double **outs, int *Hs, int *Ws);
+/* utils/warping.py:6-45 */
+int b200flow_resample_flow(b200flow_ctx*, const double *uv, int h, int w, int H, int W, double *out);
+/* utils/derivatives.py:148-296 (single-channel frames): images (H,W,2), uv (H,W,2) -> It, Ix, Iy (H,W) */
+int b200flow_partial_deriv(b200flow_ctx*, const double *images, const double *uv, int H, int W, int interp,
+                           const double filt[5], double blend, double *It, double *Ix, double *Iy);
+/* robust/penalties.py:18-345 through RobustFunction.evaluate/deriv/deriv_over_x (robust_function.py:90-128) */
+int b200flow_robust_eval(b200flow_ctx*, b200flow_penalty pen, int d_type, const double *x, long long n, double *y);
+/* flow_operator (+ the GNC blend) kept matrix-free: Ax = A@x and b, both (H,W,2); x, duv may be NULL.
+ * (classic_nl.py:279-378, ba.py:208-302, hs.py:144-203) */
+int b200flow_operator_apply(b200flow_ctx*, const b200flow_params*, double alpha, const double *uv, const double *duv,
+                            const double *It, const double *Ix, const double *Iy, int H, int W,
+                            const double *x, double *Ax, double *b, double *diag);
+/* flow_operator + _solve_linear_system (base.py:87-136): x (H,W,2), unclipped */
+int b200flow_solve_increment(b200flow_ctx*, const b200flow_params*, double alpha, const double *uv, const double *duv,
+                             const double *It, const double *Ix, const double *Iy, int H, int W,
+                             double *x, int *iters, double *relres);
+/* scipy.ndimage.median_filter(size=[kh,kw], mode='reflect') call sites hs.py:96-97,139-140; ba.py:198-199; applied to u and v */
+int b200flow_median_filter(b200flow_ctx*, const double *uv, int H, int W, int kh, int kw, double *out);
+/* utils/occlusion.py:6-56 */
+int b200flow_detect_occlusion(b200flow_ctx*, const double *uv, const double *images, int H, int W,
+                              double sigma_d, double sigma_i, double *occ);
+/* utils/weighted_median.py:24-112: uv (H,W,2), color (H,W,C) C in {1,3}, occ (H,W) -> out (H,W,2) */
+int b200flow_weighted_median(b200flow_ctx*, const double *uv, const double *color, const double *occ,
+                             int H, int W, int C, int hsz, double sigma_i, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FLOW_H */

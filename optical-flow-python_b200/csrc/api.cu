@@ -1,0 +1,442 @@
+// api.cu -- the extern "C" surface declared in include/b200flow.h.  Host-pointer entry points stage their
+// arguments through the context arena on the context stream; there is no CPU implementation behind any of
+// them: without a usable sm_100 device b200flow_ctx_create fails and nothing else can be called.
+#include "kernels.cuh"
+
+namespace bf {
+PenaltySet make_penalty_set(const b200flow_params *p, double alpha);
+int alloc_linsys(b200flow_ctx *ctx, int B, int H, int W, LinSys *s);
+}  // namespace bf
+
+using namespace bf;
+
+static std::string g_create_err;
+
+#define API_BEGIN(ctx)                                                      \
+  if (!(ctx)) return B200FLOW_EINVAL;                                       \
+  if (cudaSetDevice((ctx)->device) != cudaSuccess) return set_err((ctx), B200FLOW_ECUDA, "cudaSetDevice failed"); \
+  arena_reset(ctx);
+
+#define API_SYNC(ctx) BF_CUDA(ctx, cudaStreamSynchronize((ctx)->stream))
+
+extern "C" {
+
+int b200flow_abi_version(void) { return B200FLOW_ABI_VERSION; }
+
+int b200flow_ctx_create(int device, b200flow_ctx **out) {
+  if (!out) return B200FLOW_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libb200flow has no CPU fallback)";
+    return B200FLOW_ECUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_err = "device index out of range";
+    return B200FLOW_EINVAL;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    return B200FLOW_ECUDA;
+  }
+  if (prop.major != 10) {
+    g_create_err = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                   "; libb200flow is built for sm_100a (B200) only";
+    return B200FLOW_ECUDA;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    return B200FLOW_ECUDA;
+  }
+  b200flow_ctx *ctx = new b200flow_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    delete ctx;
+    return B200FLOW_ECUDA;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void b200flow_ctx_destroy(b200flow_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &c : ctx->chunks) cudaFree(c.base);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *b200flow_last_error(const b200flow_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int b200flow_ctx_set_timing(b200flow_ctx *ctx, int enabled) {
+  if (!ctx) return B200FLOW_EINVAL;
+  ctx->timing = enabled != 0;
+  return 0;
+}
+
+int b200flow_ctx_sync(b200flow_ctx *ctx) {
+  if (!ctx) return B200FLOW_EINVAL;
+  API_SYNC(ctx);
+  return 0;
+}
+
+void *b200flow_ctx_stream(b200flow_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int b200flow_ctx_num_sms(const b200flow_ctx *ctx) { return ctx ? ctx->num_sms : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// whole pipeline
+// ------------------------------------------------------------------------------------------------
+static int estimate_dev_impl(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C,
+                             const double *images_dev, const double *color_dev, const double *init_dev,
+                             double *uv_out_dev, b200flow_stats *stats) {
+  long long HW = (long long)H * W;
+  double *gray, *col = nullptr;
+  BF_TRY(arena_alloc(ctx, &gray, (size_t)B * 2 * HW));
+  BF_TRY(k_deinterleave(ctx, images_dev, gray, B, HW, 2));
+  if (color_dev && C > 0) {
+    BF_TRY(arena_alloc(ctx, &col, (size_t)B * C * HW));
+    BF_TRY(k_deinterleave(ctx, color_dev, col, B, HW, C));
+  }
+  return run_pipeline(ctx, p, B, H, W, C, gray, col, reinterpret_cast<const double2 *>(init_dev),
+                      reinterpret_cast<double2 *>(uv_out_dev), stats);
+}
+
+int b200flow_estimate_dev(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C,
+                          const double *images_dev, const double *color_dev, const double *init_dev,
+                          double *uv_out_dev, b200flow_stats *stats) {
+  API_BEGIN(ctx);
+  if (!images_dev || !uv_out_dev) return set_err(ctx, B200FLOW_EINVAL, "images / uv_out is NULL");
+  BF_TRY(estimate_dev_impl(ctx, p, B, H, W, C, images_dev, color_dev, init_dev, uv_out_dev, stats));
+  return 0;
+}
+
+int b200flow_estimate(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C, const double *images,
+                      const double *color, const double *init, double *uv_out, b200flow_stats *stats) {
+  API_BEGIN(ctx);
+  if (!images || !uv_out) return set_err(ctx, B200FLOW_EINVAL, "images / uv_out is NULL");
+  if (B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad batch/size B=%d H=%d W=%d", B, H, W);
+  size_t N = (size_t)B * H * W;
+  double *d_img, *d_col = nullptr, *d_init = nullptr, *d_out;
+  BF_TRY(upload(ctx, &d_img, images, 2 * N));
+  if (color && C > 0) BF_TRY(upload(ctx, &d_col, color, (size_t)C * N));
+  if (init) BF_TRY(upload(ctx, &d_init, init, 2 * N));
+  BF_TRY(arena_alloc(ctx, &d_out, 2 * N));
+  BF_TRY(estimate_dev_impl(ctx, p, B, H, W, C, d_img, d_col, d_init, d_out, stats));
+  BF_TRY(download(ctx, uv_out, d_out, 2 * N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+static int estimate_rgb8_dev_impl(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W,
+                                  const unsigned char *rgb1, const unsigned char *rgb2, int use_color,
+                                  double *uv_out_dev, b200flow_stats *stats) {
+  long long HW = (long long)H * W;
+  double *gray, *lab = nullptr, *labs = nullptr;
+  BF_TRY(arena_alloc(ctx, &gray, (size_t)B * 2 * HW));
+  if (use_color) {
+    BF_TRY(arena_alloc(ctx, &lab, (size_t)B * 3 * HW));
+    BF_TRY(arena_alloc(ctx, &labs, (size_t)B * 3 * HW));
+  }
+  BF_TRY(k_rgb8_to_gray_lab(ctx, rgb1, rgb2, B, HW, gray, lab));
+  if (use_color) BF_TRY(k_minmax_scale(ctx, lab, labs, B * 3, HW, 0.0, 255.0));   // each Lab channel separately (interface.py:59-60)
+  return run_pipeline(ctx, p, B, H, W, use_color ? 3 : 0, gray, labs, nullptr, reinterpret_cast<double2 *>(uv_out_dev),
+                      stats);
+}
+
+int b200flow_estimate_rgb8_dev(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W,
+                               const unsigned char *rgb1_dev, const unsigned char *rgb2_dev, int use_color,
+                               double *uv_out_dev, b200flow_stats *stats) {
+  API_BEGIN(ctx);
+  if (!rgb1_dev || !rgb2_dev || !uv_out_dev) return set_err(ctx, B200FLOW_EINVAL, "NULL argument");
+  BF_TRY(estimate_rgb8_dev_impl(ctx, p, B, H, W, rgb1_dev, rgb2_dev, use_color, uv_out_dev, stats));
+  return 0;
+}
+
+int b200flow_estimate_rgb8(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, const unsigned char *rgb1,
+                           const unsigned char *rgb2, int use_color, double *uv_out, b200flow_stats *stats) {
+  API_BEGIN(ctx);
+  if (!rgb1 || !rgb2 || !uv_out) return set_err(ctx, B200FLOW_EINVAL, "NULL argument");
+  if (B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad batch/size B=%d H=%d W=%d", B, H, W);
+  size_t N = (size_t)B * H * W;
+  unsigned char *d1, *d2;
+  double *d_out;
+  BF_TRY(upload(ctx, &d1, rgb1, 3 * N));
+  BF_TRY(upload(ctx, &d2, rgb2, 3 * N));
+  BF_TRY(arena_alloc(ctx, &d_out, 2 * N));
+  BF_TRY(estimate_rgb8_dev_impl(ctx, p, B, H, W, d1, d2, use_color, d_out, stats));
+  BF_TRY(download(ctx, uv_out, d_out, 2 * N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level entry points (host pointers)
+// ------------------------------------------------------------------------------------------------
+int b200flow_rgb2gray(b200flow_ctx *ctx, const double *rgb, int H, int W, double *gray) {
+  API_BEGIN(ctx);
+  size_t N = (size_t)H * W;
+  double *d_in, *d_out;
+  BF_TRY(upload(ctx, &d_in, rgb, 3 * N));
+  BF_TRY(arena_alloc(ctx, &d_out, N));
+  BF_TRY(k_rgbf_to_gray(ctx, d_in, (long long)N, d_out));
+  BF_TRY(download(ctx, gray, d_out, N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_rgb2lab(b200flow_ctx *ctx, const double *rgb, int H, int W, int scale_channels, double *lab) {
+  API_BEGIN(ctx);
+  size_t N = (size_t)H * W;
+  double *d_in, *d_lab, *d_s, *d_out;
+  BF_TRY(upload(ctx, &d_in, rgb, 3 * N));
+  BF_TRY(arena_alloc(ctx, &d_lab, 3 * N));
+  BF_TRY(arena_alloc(ctx, &d_s, 3 * N));
+  BF_TRY(arena_alloc(ctx, &d_out, 3 * N));
+  BF_TRY(k_rgbf_to_lab(ctx, d_in, (long long)N, d_lab));
+  if (scale_channels) BF_TRY(k_minmax_scale(ctx, d_lab, d_s, 3, (long long)N, 0.0, 255.0));
+  BF_TRY(k_interleave(ctx, scale_channels ? d_s : d_lab, d_out, 1, (long long)N, 3));
+  BF_TRY(download(ctx, lab, d_out, 3 * N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_scale_image(b200flow_ctx *ctx, const double *in, long long n, double lo, double hi, double *out) {
+  API_BEGIN(ctx);
+  if (n < 0) return set_err(ctx, B200FLOW_EINVAL, "n < 0");
+  if (n == 0) return 0;
+  double *d_in, *d_out;
+  BF_TRY(upload(ctx, &d_in, in, (size_t)n));
+  BF_TRY(arena_alloc(ctx, &d_out, (size_t)n));
+  BF_TRY(k_minmax_scale(ctx, d_in, d_out, 1, n, lo, hi));
+  BF_TRY(download(ctx, out, d_out, (size_t)n));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_rof_texture(b200flow_ctx *ctx, const double *img, int H, int W, int C, double theta, int iters, double alp,
+                         double *out) {
+  API_BEGIN(ctx);
+  if (H < 1 || W < 1 || C < 1 || iters < 0) return set_err(ctx, B200FLOW_EINVAL, "bad ROF arguments");
+  size_t N = (size_t)H * W;
+  double *d_in, *d_pl, *d_tex, *d_out;
+  BF_TRY(upload(ctx, &d_in, img, C * N));
+  BF_TRY(arena_alloc(ctx, &d_pl, C * N));
+  BF_TRY(arena_alloc(ctx, &d_tex, C * N));
+  BF_TRY(arena_alloc(ctx, &d_out, C * N));
+  BF_TRY(k_deinterleave(ctx, d_in, d_pl, 1, (long long)N, C));
+  BF_TRY(k_rof_texture(ctx, d_pl, d_tex, 1, C, H, W, theta, iters, alp));
+  BF_TRY(k_interleave(ctx, d_tex, d_out, 1, (long long)N, C));
+  BF_TRY(download(ctx, out, d_out, C * N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_pyramid(b200flow_ctx *ctx, const double *img, int H, int W, int C, int levels, const double *f, int fs,
+                     double ratio, double **outs, int *Hs, int *Ws) {
+  API_BEGIN(ctx);
+  if (H < 1 || W < 1 || C < 1 || levels < 1 || !Hs || !Ws) return set_err(ctx, B200FLOW_EINVAL, "bad pyramid arguments");
+  if (!(ratio > 0.0) || ratio > 1.0) return set_err(ctx, B200FLOW_EINVAL, "ratio %g out of range (0, 1]", ratio);
+  Hs[0] = H; Ws[0] = W;
+  for (int l = 1; l < levels; ++l) { Hs[l] = level_size(Hs[l - 1], ratio); Ws[l] = level_size(Ws[l - 1], ratio); }
+  if (!outs) return 0;
+  if (levels > 1 && (!f || fs < 1 || fs > 9 || (fs & 1) == 0))
+    return set_err(ctx, B200FLOW_EINVAL, "pyramid filter must be an odd square kernel of size <= 9, got %d", fs);
+  size_t N = (size_t)H * W;
+  double *d_in, *prev;
+  BF_TRY(upload(ctx, &d_in, img, C * N));
+  BF_TRY(arena_alloc(ctx, &prev, C * N));
+  BF_TRY(k_deinterleave(ctx, d_in, prev, 1, (long long)N, C));
+  if (outs[0]) BF_TRY(download(ctx, outs[0], d_in, C * N));   // level 0 is an exact copy
+  for (int l = 1; l < levels; ++l) {
+    double *cur;
+    size_t n = (size_t)Hs[l] * Ws[l];
+    BF_TRY(arena_alloc(ctx, &cur, C * n));
+    BF_TRY(k_gauss_resize(ctx, prev, cur, C, Hs[l - 1], Ws[l - 1], Hs[l], Ws[l], f, fs));
+    if (outs[l]) {
+      double *il;
+      BF_TRY(arena_alloc(ctx, &il, C * n));
+      BF_TRY(k_interleave(ctx, cur, il, 1, (long long)n, C));
+      BF_TRY(download(ctx, outs[l], il, C * n));
+    }
+    prev = cur;
+  }
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_resample_flow(b200flow_ctx *ctx, const double *uv, int h, int w, int H, int W, double *out) {
+  API_BEGIN(ctx);
+  if (h < 1 || w < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad resample sizes");
+  double *d_in, *d_out;
+  BF_TRY(upload(ctx, &d_in, uv, (size_t)2 * h * w));
+  BF_TRY(arena_alloc(ctx, &d_out, (size_t)2 * H * W));
+  BF_TRY(k_resample_flow(ctx, (const double2 *)d_in, (double2 *)d_out, 1, h, w, H, W));
+  BF_TRY(download(ctx, out, d_out, (size_t)2 * H * W));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_partial_deriv(b200flow_ctx *ctx, const double *images, const double *uv, int H, int W, int interp,
+                           const double filt[5], double blend, double *It, double *Ix, double *Iy) {
+  API_BEGIN(ctx);
+  if (interp < 0 || interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", interp);
+  if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
+  size_t N = (size_t)H * W;
+  double *d_img, *d_pl, *d_uv, *I1x, *I1y, *dIt, *dIx, *dIy;
+  double4 *src2;
+  BF_TRY(upload(ctx, &d_img, images, 2 * N));
+  BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
+  BF_TRY(arena_alloc(ctx, &d_pl, 2 * N));
+  BF_TRY(arena_alloc(ctx, &I1x, N));
+  BF_TRY(arena_alloc(ctx, &I1y, N));
+  BF_TRY(arena_alloc(ctx, &src2, N));
+  BF_TRY(arena_alloc(ctx, &dIt, N));
+  BF_TRY(arena_alloc(ctx, &dIx, N));
+  BF_TRY(arena_alloc(ctx, &dIy, N));
+  BF_TRY(k_deinterleave(ctx, d_img, d_pl, 1, (long long)N, 2));
+  BF_TRY(k_level_prep(ctx, d_pl, d_pl + N, 2 * (long long)N, 1, H, W, interp, filt, I1x, I1y, src2));
+  PenaltySet ps;
+  memset(&ps, 0, sizeof ps);
+  LinSys none;
+  memset(&none, 0, sizeof none);
+  BF_TRY(k_warp_assemble(ctx, d_pl, 2 * (long long)N, I1x, I1y, src2, (const double2 *)d_uv, nullptr, 1, H, W, interp,
+                         blend, ps, none, dIt, dIx, dIy));
+  BF_TRY(download(ctx, It, dIt, N));
+  BF_TRY(download(ctx, Ix, dIx, N));
+  BF_TRY(download(ctx, Iy, dIy, N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_robust_eval(b200flow_ctx *ctx, b200flow_penalty pen, int d_type, const double *x, long long n, double *y) {
+  API_BEGIN(ctx);
+  if (n < 0) return set_err(ctx, B200FLOW_EINVAL, "n < 0");
+  if (pen.kind < 0 || pen.kind > 9) return set_err(ctx, B200FLOW_EINVAL, "Unknown penalty kind %d", pen.kind);
+  if (d_type < 0 || d_type > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown d_type: %d", d_type);
+  if (n == 0) return 0;
+  double *d_x, *d_y;
+  BF_TRY(upload(ctx, &d_x, x, (size_t)n));
+  BF_TRY(arena_alloc(ctx, &d_y, (size_t)n));
+  BF_TRY(k_robust_eval(ctx, pen, d_type, d_x, n, d_y));
+  BF_TRY(download(ctx, y, d_y, (size_t)n));
+  API_SYNC(ctx);
+  return 0;
+}
+
+static int assemble_host(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv, const double *duv,
+                         const double *It, const double *Ix, const double *Iy, int H, int W, LinSys *sys) {
+  if (!p) return set_err(ctx, B200FLOW_EINVAL, "params is NULL");
+  if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
+  if (p->method != B200FLOW_HS && !(alpha >= 0.0 && alpha <= 1.0))
+    return set_err(ctx, B200FLOW_EINVAL, "Invalid GNC alpha: %g", alpha);
+  size_t N = (size_t)H * W;
+  double *d_uv, *d_duv = nullptr, *dIt, *dIx, *dIy;
+  BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
+  if (duv) BF_TRY(upload(ctx, &d_duv, duv, 2 * N));
+  BF_TRY(upload(ctx, &dIt, It, N));
+  BF_TRY(upload(ctx, &dIx, Ix, N));
+  BF_TRY(upload(ctx, &dIy, Iy, N));
+  BF_TRY(alloc_linsys(ctx, 1, H, W, sys));
+  PenaltySet ps = make_penalty_set(p, alpha);
+  BF_TRY(k_assemble_from_deriv(ctx, dIt, dIx, dIy, (const double2 *)d_uv, (const double2 *)d_duv, 1, H, W, ps, *sys));
+  return 0;
+}
+
+int b200flow_operator_apply(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv,
+                            const double *duv, const double *It, const double *Ix, const double *Iy, int H, int W,
+                            const double *x, double *Ax, double *b, double *diag) {
+  API_BEGIN(ctx);
+  LinSys sys;
+  BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, &sys));
+  size_t N = (size_t)H * W;
+  double *d_x = nullptr, *d_Ax = nullptr, *d_diag = nullptr;
+  if (x && Ax) {
+    BF_TRY(upload(ctx, &d_x, x, 2 * N));
+    BF_TRY(arena_alloc(ctx, &d_Ax, 2 * N));
+  }
+  if (diag) BF_TRY(arena_alloc(ctx, &d_diag, 2 * N));
+  if (d_Ax || d_diag) BF_TRY(k_operator_apply(ctx, sys, (const double2 *)d_x, (double2 *)d_Ax, (double2 *)d_diag));
+  if (d_Ax) BF_TRY(download(ctx, Ax, d_Ax, 2 * N));
+  if (d_diag) BF_TRY(download(ctx, diag, d_diag, 2 * N));
+  if (b) BF_TRY(download(ctx, b, (const double *)sys.rhs, 2 * N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_solve_increment(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv,
+                             const double *duv, const double *It, const double *Ix, const double *Iy, int H, int W,
+                             double *x, int *iters, double *relres) {
+  API_BEGIN(ctx);
+  LinSys sys;
+  BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, &sys));
+  if (!(p->tol > 0.0) || p->maxit < 1) return set_err(ctx, B200FLOW_EINVAL, "solver tol/maxit invalid");
+  if (p->solver != B200FLOW_SOLVER_EXACT && p->solver != B200FLOW_SOLVER_PCG)
+    return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
+  size_t N = (size_t)H * W;
+  PcgWork w;
+  double2 *d_x;
+  BF_TRY(pcg_work_alloc(ctx, 1, H, W, &w));
+  BF_TRY(arena_alloc(ctx, &d_x, N));
+  int rc = k_pcg_solve(ctx, sys, w, d_x, p->tol, p->maxit, p->solver == B200FLOW_SOLVER_PCG, iters, relres, true);
+  if (rc < 0 && rc != B200FLOW_ENOCONV) return rc;
+  BF_TRY(download(ctx, x, (const double *)d_x, 2 * N));
+  API_SYNC(ctx);
+  return rc;
+}
+
+int b200flow_median_filter(b200flow_ctx *ctx, const double *uv, int H, int W, int kh, int kw, double *out) {
+  API_BEGIN(ctx);
+  if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
+  size_t N = (size_t)H * W;
+  double *d_in, *d_out;
+  BF_TRY(upload(ctx, &d_in, uv, 2 * N));
+  BF_TRY(arena_alloc(ctx, &d_out, 2 * N));
+  BF_TRY(k_median_uv(ctx, (const double2 *)d_in, nullptr, 0, nullptr, (double2 *)d_out, 1, H, W, kh, kw, 1));
+  BF_TRY(download(ctx, out, d_out, 2 * N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_detect_occlusion(b200flow_ctx *ctx, const double *uv, const double *images, int H, int W, double sigma_d,
+                              double sigma_i, double *occ) {
+  API_BEGIN(ctx);
+  if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
+  size_t N = (size_t)H * W;
+  double *d_uv, *d_img, *d_pl, *d_occ;
+  BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
+  BF_TRY(upload(ctx, &d_img, images, 2 * N));
+  BF_TRY(arena_alloc(ctx, &d_pl, 2 * N));
+  BF_TRY(arena_alloc(ctx, &d_occ, N));
+  BF_TRY(k_deinterleave(ctx, d_img, d_pl, 1, (long long)N, 2));
+  BF_TRY(k_occlusion(ctx, (const double2 *)d_uv, d_pl, d_pl + N, 2 * (long long)N, 1, H, W, sigma_d, sigma_i, d_occ));
+  BF_TRY(download(ctx, occ, d_occ, N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_weighted_median(b200flow_ctx *ctx, const double *uv, const double *color, const double *occ, int H, int W,
+                             int C, int hsz, double sigma_i, double *out) {
+  API_BEGIN(ctx);
+  if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
+  if (C < 1 || C > 4) return set_err(ctx, B200FLOW_EINVAL, "weighted median supports 1..4 colour channels, got %d", C);
+  size_t N = (size_t)H * W;
+  double *d_uv, *d_col, *d_pl, *d_occ, *d_out;
+  BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
+  BF_TRY(upload(ctx, &d_col, color, C * N));
+  BF_TRY(upload(ctx, &d_occ, occ, N));
+  BF_TRY(arena_alloc(ctx, &d_pl, C * N));
+  BF_TRY(arena_alloc(ctx, &d_out, 2 * N));
+  BF_TRY(k_deinterleave(ctx, d_col, d_pl, 1, (long long)N, C));
+  BF_TRY(k_weighted_median(ctx, (const double2 *)d_uv, nullptr, d_pl, C, d_occ, 1, H, W, hsz, sigma_i, (double2 *)d_out));
+  BF_TRY(download(ctx, out, d_out, 2 * N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// common.cuh -- context, device arena, launch bookkeeping shared by every translation unit of libb200flow.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include "../../include/b200flow.h"
+
+struct b200flow_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  std::string err;
+  // grow-only device arena (bump allocation, reset per public call)
+  struct Chunk { char *base; size_t size, off; };
+  std::vector<Chunk> chunks;
+  size_t high_water = 0, in_use = 0;
+  // pinned staging for host<->device copies
+  void *pinned = nullptr;
+  size_t pinned_size = 0;
+  // statistics
+  int launches = 0;
+  bool timing = false;
+};
+
+namespace bf {
+
+inline int set_err(b200flow_ctx *ctx, int code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));
+inline int set_err(b200flow_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define BF_CUDA(ctx, call)                                                                         \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return bf::set_err((ctx), B200FLOW_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                         cudaGetErrorString(e__));                                                 \
+  } while (0)
+
+#define BF_TRY(expr)             \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ < 0) return rc__;   \
+  } while (0)
+
+// kernel launch with bookkeeping; every kernel of this library goes through here
+#define BF_LAUNCH(ctx, kern, grid, block, smem, ...)                                              \
+  do {                                                                                             \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                                 \
+    (ctx)->launches++;                                                                             \
+    cudaError_t e__ = cudaPeekAtLastError();                                                       \
+    if (e__ != cudaSuccess)                                                                        \
+      return bf::set_err((ctx), B200FLOW_ECUDA, "launch %s failed at %s:%d: %s", #kern, __FILE__,  \
+                         __LINE__, cudaGetErrorString(e__));                                       \
+  } while (0)
+
+inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- arena -------------------------------------------------------------------------------------
+inline void arena_reset(b200flow_ctx *ctx) {
+  // consolidate into one chunk sized for the high-water mark so steady state never cudaMallocs
+  if (ctx->chunks.size() > 1) {
+    size_t total = 0;
+    for (auto &c : ctx->chunks) { total += c.size; cudaFree(c.base); }
+    ctx->chunks.clear();
+    char *p = nullptr;
+    if (cudaMalloc(&p, total) == cudaSuccess) ctx->chunks.push_back({p, total, 0});
+  }
+  for (auto &c : ctx->chunks) c.off = 0;
+  ctx->in_use = 0;
+}
+
+inline void *arena_alloc_raw(b200flow_ctx *ctx, size_t bytes) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (bytes == 0) bytes = 256;
+  for (auto &c : ctx->chunks) {
+    if (c.off + bytes <= c.size) {
+      void *p = c.base + c.off;
+      c.off += bytes;
+      ctx->in_use += bytes;
+      return p;
+    }
+  }
+  size_t sz = bytes;
+  size_t grow = ctx->chunks.empty() ? (size_t(64) << 20) : ctx->chunks.back().size * 2;
+  if (sz < grow) sz = grow;
+  char *p = nullptr;
+  if (cudaMalloc(&p, sz) != cudaSuccess) {
+    sz = bytes;
+    if (cudaMalloc(&p, sz) != cudaSuccess) return nullptr;
+  }
+  ctx->chunks.push_back({p, sz, bytes});
+  ctx->in_use += bytes;
+  return p;
+}
+
+template <typename T>
+inline int arena_alloc(b200flow_ctx *ctx, T **out, size_t count) {
+  *out = static_cast<T *>(arena_alloc_raw(ctx, count * sizeof(T)));
+  if (!*out) return set_err(ctx, B200FLOW_ECUDA, "device arena: cudaMalloc of %zu bytes failed", count * sizeof(T));
+  return 0;
+}
+
+inline int ensure_pinned(b200flow_ctx *ctx, size_t bytes) {
+  if (ctx->pinned_size >= bytes) return 0;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_size = 0;
+  BF_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
+  ctx->pinned_size = bytes;
+  return 0;
+}
+
+// host -> device through the context stream (pageable source is fine; cudaMemcpyAsync stages it)
+template <typename T>
+inline int upload(b200flow_ctx *ctx, T **dev, const T *host, size_t count) {
+  BF_TRY(arena_alloc(ctx, dev, count));
+  BF_CUDA(ctx, cudaMemcpyAsync(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+template <typename T>
+inline int download(b200flow_ctx *ctx, T *host, const T *dev, size_t count) {
+  BF_CUDA(ctx, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+// ---- small device helpers -----------------------------------------------------------------------
+// scipy 'reflect' (half-sample symmetric: d c b a | a b c d | d c b a), any offset
+__host__ __device__ inline int reflect_idx(int i, int n) {
+  int p = 2 * n;
+  i %= p;
+  if (i < 0) i += p;
+  return i >= n ? p - 1 - i : i;
+}
+// whole-sample mirror (d c b | a b c d | c b a): numpy.pad 'reflect', scipy spline 'mirror'
+__host__ __device__ inline int mirror_idx(int i, int n) {
+  if (n == 1) return 0;
+  int p = 2 * (n - 1);
+  i %= p;
+  if (i < 0) i += p;
+  return i >= n ? p - i : i;
+}
+__host__ __device__ inline int clampi(int i, int lo, int hi) { return i < lo ? lo : (i > hi ? hi : i); }
+
+}  // namespace bf

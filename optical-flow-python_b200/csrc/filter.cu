@@ -1,0 +1,391 @@
+// filter.cu -- kernel group (5): median filters of the flow, occlusion confidence, and the colour- and
+// occlusion-weighted median of the Classic+NL non-local term.  Replaces scipy.ndimage.median_filter call
+// sites (hs.py:96-97,139-140; ba.py:198-199), occlusion.py:6-56 and weighted_median.py:5-112.
+// Outputs of both medians are always one of the window's input samples, selected with compare/exchange
+// networks in registers (no arithmetic on the samples), so selections are bit-exact.
+#include "kernels.cuh"
+
+namespace bf {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double clip1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }
+
+__device__ __forceinline__ void ce(double &a, double &b) {   // compare-exchange: a <= b afterwards
+  double lo = fmin(a, b), hi = fmax(a, b);
+  a = lo; b = hi;
+}
+
+// moves the minimum of v[0..K) to v[0] and the maximum to v[K-1]
+template <int K, int CAP>
+__device__ __forceinline__ void minmax_ends(double (&v)[CAP]) {
+#pragma unroll
+  for (int i = 0; i < K / 2; ++i) ce(v[i], v[K - 1 - i]);
+#pragma unroll
+  for (int i = 1; i < (K + 1) / 2; ++i) ce(v[0], v[i]);
+#pragma unroll
+  for (int i = K / 2; i < K - 1; ++i) ce(v[i], v[K - 1]);
+}
+
+// "forgetful selection" of the median of N = 2m+1 samples: keep m+2 candidates, repeatedly drop the
+// extremes and take in one more sample.  ~1.5 K compare-exchanges per step, all in registers.
+template <int K, int CAP, typename Next>
+__device__ __forceinline__ double forget_select(double (&v)[CAP], Next next, int taken) {
+  minmax_ends<K, CAP>(v);
+  if constexpr (K == 3) {
+    return v[1];
+  } else {
+    v[0] = v[K - 2];          // compact: drop min (slot 0) and max (slot K-1)
+    v[K - 2] = next(taken);
+    return forget_select<K - 1, CAP>(v, next, taken + 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// KxK median of u and v with scipy 'reflect' boundary.  Candidate field = base (+ clip(x)).
+//   assign_direct = 0: out = base + (median - base)   (ba.py:186-204: duv = filtered - uv0; uv = uv0 + duv)
+//   assign_direct = 1: out = median                    (hs.py:134-140, 95-97)
+//   active[b] == 0  : out = base                       (Horn-Schunck early exit, hs.py:126-127)
+// algorithmic bytes per pixel: read 16 (+16 for x) , write 16
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) median_kernel(const double2 *__restrict__ base, const double2 *__restrict__ x,
+                                                     int limit_update, const int *__restrict__ active,
+                                                     double2 *__restrict__ out, int H, int W, int assign_direct) {
+  constexpr int R = K / 2, TW = 32, TH = 8, SW = TW + 2 * R, SH = TH + 2 * R, N = K * K, CAP = N / 2 + 2;
+  __shared__ double2 tile[SH * SW];
+  const int b = blockIdx.z;
+  const long long off = (long long)b * H * W;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const bool act = active ? active[b] != 0 : true;
+  for (int t = threadIdx.x; t < SH * SW; t += 256) {
+    int sy = t / SW, sx = t % SW;
+    int gy = reflect_idx(y0 + sy - R, H), gx = reflect_idx(x0 + sx - R, W);
+    long long gi = off + (long long)gy * W + gx;
+    double2 v = base[gi];
+    if (x && act) {
+      double2 d = x[gi];
+      if (limit_update) { d.x = clip1(d.x); d.y = clip1(d.y); }
+      v.x += d.x; v.y += d.y;
+    }
+    tile[t] = v;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int px = x0 + lx, py = y0 + ly;
+  if (px >= W || py >= H) return;
+  long long gi = off + (long long)py * W + px;
+  double2 bs = base[gi];
+  if (!act) { out[gi] = bs; return; }
+  double2 med;
+#pragma unroll
+  for (int comp = 0; comp < 2; ++comp) {
+    auto sample = [&](int e) -> double {
+      int dy = e / K, dx = e - dy * K;
+      double2 s = tile[(ly + dy) * SW + lx + dx];
+      return comp == 0 ? s.x : s.y;
+    };
+    double v[CAP];
+#pragma unroll
+    for (int e = 0; e < CAP; ++e) v[e] = sample(e);
+    double m = forget_select<CAP, CAP>(v, sample, CAP);
+    if (comp == 0) med.x = m; else med.y = m;
+  }
+  if (assign_direct) out[gi] = med;
+  else out[gi] = make_double2(bs.x + (med.x - bs.x), bs.y + (med.y - bs.y));
+}
+
+int k_median_uv(b200flow_ctx *ctx, const double2 *base, const double2 *x, int limit_update, const int *active,
+                double2 *out, int B, int H, int W, int kh, int kw, int assign_direct) {
+  if (kh != kw || (kh != 3 && kh != 5 && kh != 7))
+    return set_err(ctx, B200FLOW_EINVAL, "median_filter_size [%d,%d] unsupported (square 3, 5 or 7)", kh, kw);
+  dim3 blk(256), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
+  if (kh == 3) BF_LAUNCH(ctx, median_kernel<3>, grd, blk, 0, base, x, limit_update, active, out, H, W, assign_direct);
+  else if (kh == 5) BF_LAUNCH(ctx, median_kernel<5>, grd, blk, 0, base, x, limit_update, active, out, H, W, assign_direct);
+  else BF_LAUNCH(ctx, median_kernel<7>, grd, blk, 0, base, x, limit_update, active, out, H, W, assign_direct);
+  return 0;
+}
+
+// out = uv + clip(x)   (classic_nl.py:252-261), gated per batch item
+__global__ void clip_add_kernel(const double2 *__restrict__ uv, const double2 *__restrict__ x, int limit_update,
+                                const int *__restrict__ active, double2 *__restrict__ out, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long gi = (long long)blockIdx.y * n + i;
+  double2 v = uv[gi];
+  if (!active || active[blockIdx.y]) {
+    double2 d = x[gi];
+    if (limit_update) { d.x = clip1(d.x); d.y = clip1(d.y); }
+    v.x += d.x; v.y += d.y;
+  }
+  out[gi] = v;
+}
+
+int k_clip_add(b200flow_ctx *ctx, const double2 *uv, const double2 *x, int limit_update, const int *active,
+               double2 *out, long long n_per_item, int B) {
+  BF_LAUNCH(ctx, clip_add_kernel, dim3((unsigned)cdiv(n_per_item, 256), B), 256, 0, uv, x, limit_update, active, out,
+            n_per_item);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Horn-Schunck early exit: active[b] &= (||x_b||_2 >= 1e-3)   (hs.py:126-127), two-stage fixed-order sum
+// ------------------------------------------------------------------------------------------------
+constexpr int NORM_BLOCKS = 64;
+
+__global__ void norm_partial_kernel(const double2 *__restrict__ x, long long n, double *__restrict__ part) {
+  const double2 *p = x + (long long)blockIdx.y * n;
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double2 v = p[i];
+    s += v.x * v.x + v.y * v.y;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    part[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+__global__ void norm_gate_kernel(const double *__restrict__ part, int nblk, int *__restrict__ active) {
+  int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nblk; ++i) t += part[b * nblk + i];
+    if (sqrt(t) < 1e-3) active[b] = 0;
+  }
+}
+
+int k_hs_norm_gate(b200flow_ctx *ctx, const double2 *x, int B, long long n, int *active, double *scratch) {
+  BF_LAUNCH(ctx, norm_partial_kernel, dim3(NORM_BLOCKS, B), 256, 0, x, n, scratch);
+  BF_LAUNCH(ctx, norm_gate_kernel, B, 32, 0, scratch, NORM_BLOCKS, active);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// occlusion confidence (occlusion.py:6-56)      bytes/pixel: read uv 16 + im1 8 + im2 8, write 8 = 40
+// ------------------------------------------------------------------------------------------------
+__global__ void occlusion_kernel(const double2 *__restrict__ uv, const double *__restrict__ im1,
+                                 const double *__restrict__ im2, long long bstride, int H, int W, double sigma_d,
+                                 double sigma_i, double *__restrict__ occ) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  long long off = (long long)blockIdx.z * H * W;
+  uv += off; im1 += (long long)blockIdx.z * bstride; im2 += (long long)blockIdx.z * bstride;
+  long long i = (long long)y * W + x;
+  double2 f = uv[i];
+  double div = 0.0;
+  if (x > 0) div += f.x - uv[i - 1].x;
+  if (y > 0) div += f.y - uv[i - W].y;
+  double x2 = (double)x + f.x, y2 = (double)y + f.y;
+  double wm = (double)(W - 1), hm = (double)(H - 1);
+  x2 = x2 < 0.0 ? 0.0 : (x2 > wm ? wm : x2);      // map_coordinates mode='nearest' == clamp the coordinate
+  y2 = y2 < 0.0 ? 0.0 : (y2 > hm ? hm : y2);
+  int fx = (int)floor(x2), fy = (int)floor(y2);
+  double tx = x2 - (double)fx, ty = y2 - (double)fy;
+  int x1 = min(fx + 1, W - 1), y1 = min(fy + 1, H - 1);
+  double w2 = (1.0 - ty) * ((1.0 - tx) * im2[(long long)fy * W + fx] + tx * im2[(long long)fy * W + x1]) +
+              ty * ((1.0 - tx) * im2[(long long)y1 * W + fx] + tx * im2[(long long)y1 * W + x1]);
+  double it = fabs(w2 - im1[i]);
+  occ[off + i] = exp(-(div * div) / (2.0 * (sigma_d * sigma_d))) * exp(-(it * it) / (2.0 * (sigma_i * sigma_i)));
+}
+
+int k_occlusion(b200flow_ctx *ctx, const double2 *uv, const double *im1, const double *im2, long long bstride, int B,
+                int H, int W, double sigma_d, double sigma_i, double *occ) {
+  dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
+  BF_LAUNCH(ctx, occlusion_kernel, grd, blk, 0, uv, im1, im2, bstride, H, W, sigma_d, sigma_i, occ);
+  return 0;
+}
+
+__global__ void sub_kernel(const double2 *__restrict__ a, const double2 *__restrict__ b, double2 *__restrict__ out,
+                           long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_double2(a[i].x - b[i].x, a[i].y - b[i].y);
+}
+
+int k_sub(b200flow_ctx *ctx, const double2 *a, const double2 *b, double2 *out, long long n) {
+  BF_LAUNCH(ctx, sub_kernel, (unsigned)cdiv(n, 256), 256, 0, a, b, out, n);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// colour/occlusion weighted median over a (2 hsz+1)^2 window (weighted_median.py:24-112)
+//   one WARP per output pixel; the window's n samples live NPL per lane in registers; two key/index
+//   bitonic sorts (u, v) with warp shuffles; ordered prefix sum of the weights; first rank whose
+//   cumulative weight reaches total/2.  Tile of colour / occ / flow staged in shared memory with the
+//   NumPy 'reflect' (mirror, no edge repeat) boundary.  Compute-bound: ~2 x 36 bitonic stages of 256 keys.
+// ------------------------------------------------------------------------------------------------
+constexpr int WM_TW = 16, WM_TH = 8, WM_WARPS = 8;
+
+template <int NPL>
+__device__ __forceinline__ void bitonic_sort_warp(double (&key)[NPL], int (&idx)[NPL], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * NPL; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= NPL) {                       // partner element lives in lane ^ (j / NPL), same register slot
+        const int lj = j / NPL;
+        const bool lower = (lane & lj) == 0;
+        const bool asc = ((lane * NPL) & k) == 0;
+        const bool want_min = lower == asc;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          double pk = __shfl_xor_sync(0xffffffffu, key[r], lj);
+          int pi = __shfl_xor_sync(0xffffffffu, idx[r], lj);
+          bool take = want_min ? (pk < key[r]) : (pk > key[r]);
+          key[r] = take ? pk : key[r];
+          idx[r] = take ? pi : idx[r];
+        }
+      } else {                              // both elements in this lane's registers
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          if ((r & j) == 0) {
+            const int r2 = r | j;
+            const bool asc = (((lane * NPL + r) & k) == 0);
+            bool sw = asc ? (key[r] > key[r2]) : (key[r] < key[r2]);
+            double ka = key[r], kb = key[r2];
+            int ia = idx[r], ib = idx[r2];
+            key[r] = sw ? kb : ka; key[r2] = sw ? ka : kb;
+            idx[r] = sw ? ib : ia; idx[r2] = sw ? ia : ib;
+          }
+        }
+      }
+    }
+  }
+}
+
+// after the sort lane L holds ranks L*NPL .. L*NPL+NPL-1; returns the weighted median (all lanes)
+template <int NPL>
+__device__ __forceinline__ double select_weighted(const double (&key)[NPL], const int (&idx)[NPL],
+                                                  const double *__restrict__ wbuf, int lane) {
+  double c[NPL];
+  double run = 0.0;
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) { run += wbuf[idx[r]]; c[r] = run; }
+  double incl = run;                          // inclusive scan of lane totals, fixed order
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  double total = __shfl_sync(0xffffffffu, incl, 31);
+  double prev = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive prefix = left neighbour's inclusive value
+  double excl = lane == 0 ? 0.0 : prev;
+  double half = total / 2.0;
+  double cand = key[NPL - 1];
+  bool found = false;
+#pragma unroll
+  for (int r = NPL - 1; r >= 0; --r) {
+    if (excl + c[r] >= half) { cand = key[r]; found = true; }
+  }
+  unsigned m = __ballot_sync(0xffffffffu, found);
+  int src = m ? __ffs(m) - 1 : 31;
+  return __shfl_sync(0xffffffffu, cand, src);
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(WM_WARPS * 32) wmedian_kernel(const double2 *__restrict__ cand,
+                                                               const double2 *__restrict__ base,
+                                                               const double *__restrict__ color, int C,
+                                                               const double *__restrict__ occ, int H, int W, int hsz,
+                                                               double inv2s2, double2 *__restrict__ out) {
+  extern __shared__ double smem[];
+  const int wsz = 2 * hsz + 1, n = wsz * wsz;
+  const int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz, SN = SW * SH;
+  double2 *s_uv = reinterpret_cast<double2 *>(smem);          // [SN]
+  double *s_occ = smem + 2 * SN;                               // [SN]
+  double *s_col = s_occ + SN;                                  // [C][SN]
+  double *s_w = s_col + (size_t)C * SN;                        // [WM_WARPS][32*NPL]
+  const int b = blockIdx.z;
+  const long long HW = (long long)H * W, off = (long long)b * HW;
+  const int x0 = blockIdx.x * WM_TW, y0 = blockIdx.y * WM_TH;
+  for (int t = threadIdx.x; t < SN; t += blockDim.x) {
+    int sy = t / SW, sx = t - sy * SW;
+    int gy = mirror_idx(y0 + sy - hsz, H), gx = mirror_idx(x0 + sx - hsz, W);
+    long long gi = (long long)gy * W + gx;
+    s_uv[t] = cand[off + gi];
+    s_occ[t] = occ[off + gi];
+    for (int c = 0; c < C; ++c) s_col[c * SN + t] = color[((long long)b * C + c) * HW + gi];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *wbuf = s_w + warp * 32 * NPL;
+  const int py = y0 + warp;
+  if (py >= H) return;
+  for (int lx = 0; lx < WM_TW; ++lx) {
+    const int px = x0 + lx;
+    if (px >= W) break;
+    const int ctr = (warp + hsz) * SW + lx + hsz;
+    double ku[NPL], kv[NPL];
+    int iu[NPL], iv[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      int e = k * 32 + lane;
+      double w = 0.0;
+      ku[k] = INFINITY; kv[k] = INFINITY;
+      if (e < n) {
+        int dy = e / wsz, dx = e - dy * wsz;
+        int q = (warp + dy) * SW + lx + dx;
+        double cd = 0.0;
+        for (int c = 0; c < C; ++c) {
+          double d = s_col[c * SN + q] - s_col[c * SN + ctr];
+          cd += d * d;
+        }
+        w = fmax(exp(-cd * inv2s2) * s_occ[q], 1e-10);
+        double2 f = s_uv[q];
+        ku[k] = f.x; kv[k] = f.y;
+      }
+      iu[k] = e; iv[k] = e;
+      wbuf[e] = w;
+    }
+    __syncwarp();
+    bitonic_sort_warp<NPL>(ku, iu, lane);
+    double mu = select_weighted<NPL>(ku, iu, wbuf, lane);
+    bitonic_sort_warp<NPL>(kv, iv, lane);
+    double mv = select_weighted<NPL>(kv, iv, wbuf, lane);
+    __syncwarp();
+    if (lane == 0) {
+      long long gi = off + (long long)py * W + px;
+      if (base) {
+        double2 bs = base[gi];
+        out[gi] = make_double2(bs.x + (mu - bs.x), bs.y + (mv - bs.y));
+      } else {
+        out[gi] = make_double2(mu, mv);
+      }
+    }
+  }
+}
+
+template <int NPL>
+static int launch_wmedian(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color, int C,
+                          const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
+  int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
+  size_t smem = (size_t)SW * SH * (3 + C) * sizeof(double) + (size_t)WM_WARPS * 32 * NPL * sizeof(double);
+  if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
+  BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
+  double inv2s2 = 1.0 / (2.0 * (sigma_i * sigma_i));
+  BF_LAUNCH(ctx, wmedian_kernel<NPL>, grd, WM_WARPS * 32, smem, cand, base, color, C, occ, H, W, hsz, inv2s2, out);
+  return 0;
+}
+
+int k_weighted_median(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color, int C,
+                      const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
+  if (hsz < 0) return set_err(ctx, B200FLOW_EINVAL, "area_hsz must be >= 0");
+  if (C < 1 || C > 4) return set_err(ctx, B200FLOW_EINVAL, "weighted median supports 1..4 colour channels, got %d", C);
+  int n = (2 * hsz + 1) * (2 * hsz + 1);
+  if (n <= 32) return launch_wmedian<1>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n <= 64) return launch_wmedian<2>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n <= 128) return launch_wmedian<4>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n <= 256) return launch_wmedian<8>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n <= 512) return launch_wmedian<16>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  return set_err(ctx, B200FLOW_EINVAL, "area_hsz=%d (window %d samples) unsupported (max 10)", hsz, n);
+}
+
+}  // namespace bf

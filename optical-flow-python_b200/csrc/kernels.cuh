@@ -1,0 +1,95 @@
+// kernels.cuh -- device-level (all pointers are DEVICE pointers, every routine is batch-aware) launchers.
+// Data layout in HBM:
+//   image planes   double [P][H][W]            P = B*C planes, planar (de-interleaved on upload)
+//   flow / vectors double2[B][H][W]            (u,v) interleaved = one 16-byte load per pixel
+//   warp source    double4[B][H][W]            Hermite: {Z, DX, DY, DXY} of frame 2; spline/bilinear:
+//                                              {c(I2), c(I2x), c(I2y), 0} -> one 32-byte sector per tap
+//   linear system  D  double2 {a11,a22}, a12 double, WH double2 {wuh,wvh}, WV double2 {wuv,wvv},
+//                  rhs double2 {bu,bv}
+#pragma once
+#include "common.cuh"
+
+namespace bf {
+
+struct PenaltySet {            // everything the assemble kernel needs to form the GNC-blended IRLS weights
+  b200flow_penalty rho_su[2], rho_sv[2], rho_d, qua_su[2], qua_sv[2], qua_d;
+  double lambda, lambda_q, alpha;
+  int hs;                      // 1: Horn-Schunck form (unit weights * lambda/sigmaS2, d = 1/sigmaD2)
+  double hs_w, hs_d;
+};
+
+struct LinSys {                // matrix-free 2N x 2N system, B systems of H x W pixels
+  int B, H, W;
+  double2 *D;                  // {a11, a22}
+  double *a12;
+  double2 *WH, *WV;            // {wuh, wvh}, {wuv, wvv}
+  double2 *rhs;
+};
+
+struct PcgWork {               // scratch vectors + reduction buffers for the persistent PCG kernel
+  double2 *r, *p, *Ap;
+  double *Minv;                // 3 planes: m11, m12, m22 (block-Jacobi inverse) [3][B*H*W]
+  double *partial;             // [3][B][grid]
+  double *scal;                // per-system scalars [8][B]
+  int *flags;                  // [0]=ndone, [1..B]=done[b], then iters[b]
+  int grid;
+};
+
+// ---- pre.cu
+int k_deinterleave(b200flow_ctx *, const double *src, double *dst, int B, long long HW, int C);
+int k_interleave(b200flow_ctx *, const double *src, double *dst, int B, long long HW, int C);
+int k_minmax_scale(b200flow_ctx *, const double *in, double *out, int items, long long n, double lo, double hi);
+int k_rof_texture(b200flow_ctx *, const double *img, double *out, int B, int C, int H, int W, double theta,
+                  int iters, double alp);
+int k_gauss_resize(b200flow_ctx *, const double *src, double *dst, int P, int H, int W, int Hn, int Wn,
+                   const double *taps, int ks);
+int k_resample_flow(b200flow_ctx *, const double2 *in, double2 *out, int B, int h, int w, int H, int W);
+int k_rgb8_to_gray_lab(b200flow_ctx *, const unsigned char *rgb1, const unsigned char *rgb2, int B, long long HW,
+                       double *gray /*[B][2][HW]*/, double *lab /*[B][3][HW] or null*/);
+int k_rgbf_to_gray(b200flow_ctx *, const double *rgb, long long HW, double *gray);
+int k_rgbf_to_lab(b200flow_ctx *, const double *rgb, long long HW, double *lab /*[3][HW]*/);
+void gaussian_taps(double spacing, double *taps /*>=81*/, int *ks);
+int level_size(int n, double ratio);
+int auto_levels(int H, int W, double spacing);
+
+// ---- warp.cu
+// im1/im2 point at the first pair's frames; pair b's frames are bstride doubles further on ([B][2][H][W] layout)
+int k_level_prep(b200flow_ctx *, const double *im1, const double *im2, long long bstride, int B, int H, int W,
+                 int interp, const double filt[5], double *I1x, double *I1y, double4 *src2);
+int k_warp_assemble(b200flow_ctx *, const double *im1, long long bstride, const double *I1x, const double *I1y,
+                    const double4 *src2,
+                    const double2 *uv, const double2 *duv, int B, int H, int W, int interp, double blend,
+                    const PenaltySet &ps, LinSys sys, double *It, double *Ix, double *Iy);
+// assemble from given derivative planes (operator_apply / solve_increment entry points, max_linear>1 re-linearisation)
+int k_assemble_from_deriv(b200flow_ctx *, const double *It, const double *Ix, const double *Iy, const double2 *uv,
+                          const double2 *duv, int B, int H, int W, const PenaltySet &ps, LinSys sys);
+int k_robust_eval(b200flow_ctx *, b200flow_penalty pen, int d_type, const double *x, long long n, double *y);
+
+// ---- solve.cu
+size_t pcg_work_bytes(const b200flow_ctx *, int B, int H, int W);
+int pcg_work_alloc(b200flow_ctx *, int B, int H, int W, PcgWork *w);
+int k_pcg_solve(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int scalar_jacobi,
+                int *iters_host /*[B] or null*/, double *relres_host /*[B] or null*/, bool sync_results);
+int k_pcg_solve_async(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int scalar_jacobi,
+                      long long *stats_dev);
+int k_operator_apply(b200flow_ctx *, LinSys sys, const double2 *x, double2 *Ax, double2 *diag);
+
+// ---- filter.cu
+// out = base + (median(base + clip(x)) - base) when x != null (BA update, ba.py:186-204), else out = median(base)
+int k_median_uv(b200flow_ctx *, const double2 *base, const double2 *x, int limit_update, const int *active,
+                double2 *out, int B, int H, int W, int kh, int kw, int assign_direct);
+int k_clip_add(b200flow_ctx *, const double2 *uv, const double2 *x, int limit_update, const int *active, double2 *out,
+               long long n_per_item, int B);
+int k_occlusion(b200flow_ctx *, const double2 *uv, const double *im1, const double *im2, long long bstride, int B,
+                int H, int W, double sigma_d, double sigma_i, double *occ);
+int k_sub(b200flow_ctx *, const double2 *a, const double2 *b, double2 *out, long long n);
+// out = base + (wmed(cand) - base) when base != null else wmed(cand)
+int k_weighted_median(b200flow_ctx *, const double2 *cand, const double2 *base, const double *color, int C,
+                      const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out);
+int k_hs_norm_gate(b200flow_ctx *, const double2 *x, int B, long long n, int *active, double *scratch);
+
+// ---- pipeline.cu
+int run_pipeline(b200flow_ctx *, const b200flow_params *p, int B, int H, int W, int C, const double *gray_planar,
+                 const double *color_planar, const double2 *init, double2 *uv_out, b200flow_stats *stats);
+
+}  // namespace bf

@@ -1,0 +1,317 @@
+// pipeline.cu -- the coarse-to-fine control loops of the three method drivers, run natively so that a batch of
+// B same-size frame pairs needs no host<->device synchronisation between the upload and the final download.
+// Replaces HSOpticalFlow.compute_flow/compute_flow_base (hs.py:49-142), BAOpticalFlow (ba.py:57-206) and
+// ClassicNLOpticalFlow (classic_nl.py:89-277).  Every buffer is allocated once at full resolution from the
+// context arena and reused by every level / warp iteration.
+#include "kernels.cuh"
+
+namespace bf {
+
+namespace {
+
+struct Pyramid {
+  std::vector<int> H, W;
+  std::vector<double *> lv;   // lv[l]: [P][H[l]][W[l]] planes
+};
+
+int build_pyramid(b200flow_ctx *ctx, double *img, int P, int H, int W, int levels, double spacing, Pyramid *out) {
+  double taps[81];
+  int ks;
+  gaussian_taps(spacing, taps, &ks);
+  double ratio = 1.0 / spacing;
+  out->H.assign(1, H);
+  out->W.assign(1, W);
+  out->lv.assign(1, img);
+  for (int l = 1; l < levels; ++l) {
+    int h = out->H.back(), w = out->W.back();
+    int hn = level_size(h, ratio), wn = level_size(w, ratio);
+    double *dst;
+    BF_TRY(arena_alloc(ctx, &dst, (size_t)P * hn * wn));
+    BF_TRY(k_gauss_resize(ctx, out->lv.back(), dst, P, h, w, hn, wn, taps, ks));
+    out->H.push_back(hn);
+    out->W.push_back(wn);
+    out->lv.push_back(dst);
+  }
+  return 0;
+}
+
+__global__ void fill_int_kernel(int *p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// per-stage CUDA-event timing (only when ctx->timing): events are recorded on the stream and resolved once at the end
+struct StageTimer {
+  b200flow_ctx *ctx;
+  bool on;
+  struct Span { cudaEvent_t a, b; int cat; };
+  std::vector<Span> spans;
+  explicit StageTimer(b200flow_ctx *c) : ctx(c), on(c->timing) {}
+  void begin(int cat) {
+    if (!on) return;
+    Span s;
+    cudaEventCreate(&s.a);
+    cudaEventCreate(&s.b);
+    s.cat = cat;
+    cudaEventRecord(s.a, ctx->stream);
+    spans.push_back(s);
+  }
+  void end() {
+    if (!on) return;
+    cudaEventRecord(spans.back().b, ctx->stream);
+  }
+  void resolve(double ms[4]) {
+    for (int i = 0; i < 4; ++i) ms[i] = 0.0;
+    for (auto &s : spans) {
+      float t = 0.f;
+      if (on && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms[s.cat] += t;
+      cudaEventDestroy(s.a);
+      cudaEventDestroy(s.b);
+    }
+    spans.clear();
+  }
+};
+enum { T_PRE = 0, T_WARP = 1, T_SOLVE = 2, T_FILTER = 3 };
+
+int check_params(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C) {
+  if (!p) return set_err(ctx, B200FLOW_EINVAL, "params is NULL");
+  if (B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad batch/size B=%d H=%d W=%d", B, H, W);
+  if (p->method < 0 || p->method > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown method %d", p->method);
+  if (p->interp < 0 || p->interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", p->interp);
+  if (p->solver != B200FLOW_SOLVER_EXACT && p->solver != B200FLOW_SOLVER_PCG)
+    return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
+  if (!(p->pyramid_spacing > 1.0) || p->pyramid_spacing > 8.0)
+    return set_err(ctx, B200FLOW_EINVAL, "pyramid_spacing %g out of range (1, 8]", p->pyramid_spacing);
+  if (p->method != B200FLOW_HS && (!(p->gnc_pyramid_spacing > 1.0) || p->gnc_pyramid_spacing > 8.0))
+    return set_err(ctx, B200FLOW_EINVAL, "gnc_pyramid_spacing %g out of range (1, 8]", p->gnc_pyramid_spacing);
+  if (C < 0 || C > 4) return set_err(ctx, B200FLOW_EINVAL, "colour channels C=%d unsupported", C);
+  if (!(p->tol > 0.0) || p->maxit < 1) return set_err(ctx, B200FLOW_EINVAL, "solver tol/maxit invalid");
+  const b200flow_penalty *pens[] = {&p->rho_su[0], &p->rho_su[1], &p->rho_sv[0], &p->rho_sv[1], &p->rho_d,
+                                    &p->qua_su[0], &p->qua_su[1], &p->qua_sv[0], &p->qua_sv[1], &p->qua_d};
+  for (auto q : pens)
+    if (q->kind < 0 || q->kind > 9) return set_err(ctx, B200FLOW_EINVAL, "Unknown penalty kind %d", q->kind);
+  return 0;
+}
+
+}  // namespace
+
+PenaltySet make_penalty_set(const b200flow_params *p, double alpha) {
+  PenaltySet ps;
+  for (int i = 0; i < 2; ++i) {
+    ps.rho_su[i] = p->rho_su[i]; ps.rho_sv[i] = p->rho_sv[i];
+    ps.qua_su[i] = p->qua_su[i]; ps.qua_sv[i] = p->qua_sv[i];
+  }
+  ps.rho_d = p->rho_d; ps.qua_d = p->qua_d;
+  ps.lambda = p->lambda; ps.lambda_q = p->lambda_q; ps.alpha = alpha;
+  ps.hs = p->method == B200FLOW_HS;
+  ps.hs_w = p->lambda / p->sigmaS2;
+  ps.hs_d = 1.0 / p->sigmaD2;
+  return ps;
+}
+
+int alloc_linsys(b200flow_ctx *ctx, int B, int H, int W, LinSys *s) {
+  size_t n = (size_t)B * H * W;
+  s->B = B; s->H = H; s->W = W;
+  BF_TRY(arena_alloc(ctx, &s->D, n));
+  BF_TRY(arena_alloc(ctx, &s->a12, n));
+  BF_TRY(arena_alloc(ctx, &s->WH, n));
+  BF_TRY(arena_alloc(ctx, &s->WV, n));
+  BF_TRY(arena_alloc(ctx, &s->rhs, n));
+  return 0;
+}
+
+int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C, const double *gray_planar,
+                 const double *color_planar, const double2 *init, double2 *uv_out, b200flow_stats *stats) {
+  BF_TRY(check_params(ctx, p, B, H, W, C));
+  const long long HW = (long long)H * W;
+  const size_t N = (size_t)B * HW;
+  const bool hs = p->method == B200FLOW_HS, cnl = p->method == B200FLOW_CLASSICNL;
+  const int launches0 = ctx->launches;
+  StageTimer tm(ctx);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx->timing) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, ctx->stream);
+  }
+
+  // ---- pre-processing: texture or [0,255] scaling (joint over the two frames of a pair) ----
+  tm.begin(T_PRE);
+  double *pre;
+  BF_TRY(arena_alloc(ctx, &pre, 2 * N));
+  if (p->texture > 0) BF_TRY(k_rof_texture(ctx, gray_planar, pre, B, 2, H, W, p->rof_theta, p->rof_iters, p->alp));
+  else if (p->texture == 0) BF_TRY(k_minmax_scale(ctx, gray_planar, pre, B, 2 * HW, 0.0, 255.0));
+  else BF_CUDA(ctx, cudaMemcpyAsync(pre, gray_planar, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+
+  int levels = (hs || p->auto_level) ? auto_levels(H, W, p->pyramid_spacing) : p->pyramid_levels;
+  if (p->pyramid_levels > 0 && !p->auto_level) levels = p->pyramid_levels;
+  Pyramid pyr, gpyr, cpyr, gcpyr;
+  BF_TRY(build_pyramid(ctx, pre, 2 * B, H, W, levels, p->pyramid_spacing, &pyr));
+  const bool use_color = cnl && color_planar != nullptr && C > 0;
+  if (!hs) {
+    BF_TRY(build_pyramid(ctx, pre, 2 * B, H, W, p->gnc_pyramid_levels, p->gnc_pyramid_spacing, &gpyr));
+    if (use_color) {
+      BF_TRY(build_pyramid(ctx, const_cast<double *>(color_planar), C * B, H, W, levels, p->pyramid_spacing, &cpyr));
+      BF_TRY(build_pyramid(ctx, const_cast<double *>(color_planar), C * B, H, W, p->gnc_pyramid_levels,
+                           p->gnc_pyramid_spacing, &gcpyr));
+    }
+  }
+  tm.end();
+
+  // ---- work buffers at full resolution, reused by every level ----
+  double2 *uvA, *uvB, *x, *cand = nullptr, *duv = nullptr;
+  double *occ = nullptr, *I1x, *I1y, *It = nullptr, *Ix = nullptr, *Iy = nullptr, *nscratch = nullptr;
+  double4 *src2;
+  int *active = nullptr;
+  long long *dstats;
+  LinSys sys;
+  PcgWork work;
+  BF_TRY(arena_alloc(ctx, &uvA, N));
+  BF_TRY(arena_alloc(ctx, &uvB, N));
+  BF_TRY(arena_alloc(ctx, &x, N));
+  BF_TRY(arena_alloc(ctx, &I1x, N));
+  BF_TRY(arena_alloc(ctx, &I1y, N));
+  BF_TRY(arena_alloc(ctx, &src2, N));
+  BF_TRY(alloc_linsys(ctx, B, H, W, &sys));
+  BF_TRY(pcg_work_alloc(ctx, B, H, W, &work));
+  BF_TRY(arena_alloc(ctx, &dstats, 4));
+  BF_CUDA(ctx, cudaMemsetAsync(dstats, 0, 4 * sizeof(long long), ctx->stream));
+  if (cnl) {
+    BF_TRY(arena_alloc(ctx, &cand, N));
+    BF_TRY(arena_alloc(ctx, &occ, N));
+  }
+  if (hs) {
+    BF_TRY(arena_alloc(ctx, &active, (size_t)B));
+    BF_TRY(arena_alloc(ctx, &nscratch, (size_t)B * 64));
+  }
+  if (!hs && p->max_linear > 1) {
+    BF_TRY(arena_alloc(ctx, &duv, N));
+    BF_TRY(arena_alloc(ctx, &It, N));
+    BF_TRY(arena_alloc(ctx, &Ix, N));
+    BF_TRY(arena_alloc(ctx, &Iy, N));
+  }
+
+  double2 *cur = uvA, *nxt = uvB;
+  int ch = H, cw = W;     // size of the flow currently held in `cur`
+  if (init) BF_CUDA(ctx, cudaMemcpyAsync(cur, init, N * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+  else BF_CUDA(ctx, cudaMemsetAsync(cur, 0, N * sizeof(double2), ctx->stream));
+
+  const int mh = p->median_h, mw = p->median_w;
+  const bool have_median = mh > 0 && mw > 0;
+  const int scalar_jacobi = p->solver == B200FLOW_SOLVER_PCG;
+  int solves = 0;
+
+  const int gnc_stages = hs ? 1 : p->gnc_iters;
+  double alpha = p->alpha0;
+  for (int ignc = 0; ignc < gnc_stages; ++ignc) {
+    const Pyramid &ip = (ignc == 0) ? pyr : gpyr;
+    const Pyramid &cp = (ignc == 0) ? cpyr : gcpyr;
+    const int nl = (int)ip.lv.size() < ((ignc == 0) ? levels : p->gnc_pyramid_levels)
+                       ? (int)ip.lv.size() : ((ignc == 0) ? levels : p->gnc_pyramid_levels);
+    if (!hs && !(alpha >= 0.0 && alpha <= 1.0)) return set_err(ctx, B200FLOW_EINVAL, "Invalid GNC alpha: %g", alpha);
+    for (int l = nl - 1; l >= 0; --l) {
+      const int h = ip.H[l], w = ip.W[l];
+      const long long hw = (long long)h * w;
+      const double *im1 = ip.lv[l], *im2 = ip.lv[l] + hw;
+      const long long bstride = 2 * hw;
+      tm.begin(T_WARP);
+      BF_TRY(k_resample_flow(ctx, cur, nxt, B, ch, cw, h, w));
+      std::swap(cur, nxt);
+      ch = h; cw = w;
+      BF_TRY(k_level_prep(ctx, im1, im2, bstride, B, h, w, p->interp, p->deriv_filter, I1x, I1y, src2));
+      tm.end();
+      sys.H = h; sys.W = w;
+      if (hs) BF_LAUNCH(ctx, fill_int_kernel, (unsigned)cdiv(B, 128), 128, 0, active, B, 1);
+      const int warps = hs ? p->max_warping_iters : p->max_iters;
+      const int nlin = hs ? 1 : (ignc == 0 ? 1 : (p->max_linear < 1 ? 1 : p->max_linear));
+      PenaltySet ps = make_penalty_set(p, alpha);
+      for (int it = 0; it < warps; ++it) {
+        const double2 *dcur = nullptr;    // duv of the current linearisation (zero on the first pass)
+        for (int j = 0; j < nlin; ++j) {
+          tm.begin(T_WARP);
+          if (j == 0)
+            BF_TRY(k_warp_assemble(ctx, im1, bstride, I1x, I1y, src2, cur, nullptr, B, h, w, p->interp, p->blend, ps, sys,
+                                   nlin > 1 ? It : nullptr, Ix, Iy));
+          else
+            BF_TRY(k_assemble_from_deriv(ctx, It, Ix, Iy, cur, dcur, B, h, w, ps, sys));
+          tm.end();
+          tm.begin(T_SOLVE);
+          BF_TRY(k_pcg_solve_async(ctx, sys, work, x, p->tol, p->maxit, scalar_jacobi, dstats));
+          tm.end();
+          solves++;
+          tm.begin(T_FILTER);
+          if (hs) {
+            BF_TRY(k_hs_norm_gate(ctx, x, B, hw, active, nscratch));
+            if (have_median) {
+              BF_TRY(k_median_uv(ctx, cur, x, p->limit_update, active, nxt, B, h, w, mh, mw, 1));
+              for (int m = 1; m < p->mf_iter; ++m) {
+                std::swap(cur, nxt);
+                BF_TRY(k_median_uv(ctx, cur, nullptr, 0, active, nxt, B, h, w, mh, mw, 1));
+              }
+            } else {
+              BF_TRY(k_clip_add(ctx, cur, x, p->limit_update, active, nxt, hw, B));
+            }
+          } else if (cnl && have_median && use_color) {
+            BF_TRY(k_clip_add(ctx, cur, x, p->limit_update, nullptr, cand, hw, B));
+            BF_TRY(k_occlusion(ctx, cand, im1, im2, bstride, B, h, w, p->occ_sigma_d, p->occ_sigma_i, occ));
+            BF_TRY(k_weighted_median(ctx, cand, cur, cp.lv[l], C, occ, B, h, w, p->area_hsz, p->sigma_i, nxt));
+          } else if (have_median) {
+            // BA (ba.py:197-201) and Classic+NL without a usable colour image (weighted_median.py:42-47: square mfsz[0])
+            BF_TRY(k_median_uv(ctx, cur, x, p->limit_update, nullptr, nxt, B, h, w, mh, cnl ? mh : mw, 0));
+          } else {
+            BF_TRY(k_clip_add(ctx, cur, x, p->limit_update, nullptr, nxt, hw, B));
+          }
+          if (j + 1 < nlin) {               // next linearisation pass sees duv = filtered - uv
+            BF_TRY(k_sub(ctx, nxt, cur, duv, (long long)B * hw));
+            dcur = duv;
+          }
+          tm.end();
+        }
+        std::swap(cur, nxt);                 // uv = uv + duv
+      }
+    }
+    if (!hs && p->gnc_iters > 1) {
+      double na = 1.0 - (double)(ignc + 1) / (double)(p->gnc_iters - 1);
+      alpha = alpha < na ? alpha : na;
+      alpha = alpha > 0.0 ? alpha : 0.0;
+    }
+  }
+  if (ch != H || cw != W) {
+    // no level was run (min(H,W) < 16: auto levels <= 0) -- the reference returns init unchanged
+    return set_err(ctx, B200FLOW_EINVAL, "internal: final flow size %dx%d != %dx%d", ch, cw, H, W);
+  }
+  if (hs && have_median && p->final_median) {   // final median (hs.py:95-97)
+    tm.begin(T_FILTER);
+    BF_TRY(k_median_uv(ctx, cur, nullptr, 0, nullptr, nxt, B, H, W, mh, mw, 1));
+    tm.end();
+    std::swap(cur, nxt);
+  }
+  BF_CUDA(ctx, cudaMemcpyAsync(uv_out, cur, N * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->timing) cudaEventRecord(ev1, ctx->stream);
+
+  long long hstats[4] = {0, 0, 0, 0};
+  if (stats || ctx->timing) {
+    BF_CUDA(ctx, cudaMemcpyAsync(hstats, dstats, sizeof hstats, cudaMemcpyDeviceToHost, ctx->stream));
+    BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  double ms[4] = {0, 0, 0, 0};
+  tm.resolve(ms);
+  if (stats) {
+    stats->solves = solves;
+    stats->pcg_iters = hstats[0];
+    stats->not_converged = (int)hstats[1];
+    stats->pcg_pixel_iters = hstats[3];
+    stats->kernel_launches = ctx->launches - launches0;
+    stats->pre_ms = ms[T_PRE]; stats->warp_ms = ms[T_WARP]; stats->solver_ms = ms[T_SOLVE]; stats->filter_ms = ms[T_FILTER];
+    stats->total_ms = 0.0;
+    if (ctx->timing) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev0, ev1);
+      stats->total_ms = t;
+    }
+  }
+  if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+  return 0;
+}
+
+}  // namespace bf

@@ -1,0 +1,412 @@
+// pre.cu -- kernel group (1): layout changes, colour conversion, min/max scaling, ROF structure-texture
+// decomposition, Gaussian pyramid, flow resampling.  Replaces interface.py:74-141, image_processing.py:6-136,
+// pyramid.py:6-73, warping.py:6-45 of the reference.  All kernels are one-thread-per-output-element
+// streaming stencils (HBM-bound, coalesced along W); compiled with -fmad=false so that the integer-valued
+// decisions (gray quantisation, resize sample indices) round exactly like the NumPy reference.
+#include "kernels.cuh"
+
+namespace bf {
+
+// ------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------
+__global__ void deinterleave_kernel(const double *__restrict__ src, double *__restrict__ dst, long long total,
+                                    long long HW, int C) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // index into dst (B,C,HW)
+  if (i >= total) return;
+  long long px = i % HW;
+  long long t = i / HW;
+  int c = (int)(t % C);
+  long long b = t / C;
+  dst[i] = src[(b * HW + px) * C + c];
+}
+
+__global__ void interleave_kernel(const double *__restrict__ src, double *__restrict__ dst, long long total,
+                                  long long HW, int C) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // index into dst (B,HW,C)
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long t = i / C;
+  long long px = t % HW;
+  long long b = t / HW;
+  dst[i] = src[(b * C + c) * HW + px];
+}
+
+int k_deinterleave(b200flow_ctx *ctx, const double *src, double *dst, int B, long long HW, int C) {
+  long long total = (long long)B * HW * C;
+  BF_LAUNCH(ctx, deinterleave_kernel, (unsigned)cdiv(total, 256), 256, 0, src, dst, total, HW, C);
+  return 0;
+}
+int k_interleave(b200flow_ctx *ctx, const double *src, double *dst, int B, long long HW, int C) {
+  long long total = (long long)B * HW * C;
+  BF_LAUNCH(ctx, interleave_kernel, (unsigned)cdiv(total, 256), 256, 0, src, dst, total, HW, C);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// min/max scaling (scale_image, image_processing.py:6-26): exact, order-independent reduction
+// ------------------------------------------------------------------------------------------------
+constexpr int MM_BLOCKS = 64;   // partial blocks per item
+
+__global__ void minmax_partial_kernel(const double *__restrict__ in, long long n, double2 *__restrict__ part) {
+  const double *p = in + (long long)blockIdx.y * n;
+  double lo = INFINITY, hi = -INFINITY;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = p[i];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ double slo[32], shi[32];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { slo[w] = lo; shi[w] = hi; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    lo = l < nw ? slo[l] : INFINITY;
+    hi = l < nw ? shi[l] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (l == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = make_double2(lo, hi);
+  }
+}
+
+__global__ void minmax_final_kernel(const double2 *__restrict__ part, int nblk, double2 *__restrict__ mm) {
+  int item = blockIdx.x;
+  double lo = INFINITY, hi = -INFINITY;
+  for (int i = threadIdx.x; i < nblk; i += 32) {
+    double2 v = part[item * nblk + i];
+    lo = fmin(lo, v.x);
+    hi = fmax(hi, v.y);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (threadIdx.x == 0) mm[item] = make_double2(lo, hi);
+}
+
+__global__ void scale_apply_kernel(const double *__restrict__ in, double *__restrict__ out, long long n,
+                                   const double2 *__restrict__ mm, double lo, double hi) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int item = blockIdx.y;
+  double2 m = mm[item];
+  long long o = (long long)item * n + i;
+  double v;
+  if (m.y == m.x) v = (lo + hi) / 2.0;
+  else v = (in[o] - m.x) / (m.y - m.x) * (hi - lo) + lo;
+  out[o] = v;
+}
+
+static int minmax_items(b200flow_ctx *ctx, const double *in, int items, long long n, double2 **mm_out) {
+  double2 *part, *mm;
+  int nblk = (int)std::min<long long>(MM_BLOCKS, std::max<long long>(1, cdiv(n, 1024)));
+  BF_TRY(arena_alloc(ctx, &part, (size_t)items * nblk));
+  BF_TRY(arena_alloc(ctx, &mm, (size_t)items));
+  BF_LAUNCH(ctx, minmax_partial_kernel, dim3(nblk, items), 256, 0, in, n, part);
+  BF_LAUNCH(ctx, minmax_final_kernel, items, 32, 0, part, nblk, mm);
+  *mm_out = mm;
+  return 0;
+}
+
+int k_minmax_scale(b200flow_ctx *ctx, const double *in, double *out, int items, long long n, double lo, double hi) {
+  if (items <= 0 || n <= 0) return 0;
+  double2 *mm;
+  BF_TRY(minmax_items(ctx, in, items, n, &mm));
+  BF_LAUNCH(ctx, scale_apply_kernel, dim3((unsigned)cdiv(n, 256), items), 256, 0, in, out, n, mm, lo, hi);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROF structure-texture decomposition (image_processing.py:52-136)
+//   per iteration:  u = im + theta*div p ;  p += delta*grad u ;  p /= max(1,|p|)
+//   algorithmic bytes per pixel per iteration: read im 8 + p 16, write p 16 = 40 B
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rof_div(const double2 *__restrict__ p, int y, int x, int W) {
+  // backward differences with the reference's boundary rule: first column / row use p itself
+  double2 c = p[(long long)y * W + x];
+  double dx = x > 0 ? c.x - p[(long long)y * W + x - 1].x : c.x;
+  double dy = y > 0 ? c.y - p[(long long)(y - 1) * W + x].y : c.y;
+  return dx + dy;
+}
+
+__global__ void rof_iter_kernel(const double *__restrict__ im, const double2 *__restrict__ pin,
+                                double2 *__restrict__ pout, int H, int W, double theta, double delta) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  long long off = (long long)blockIdx.z * H * W;
+  im += off; pin += off; pout += off;
+  long long i = (long long)y * W + x;
+  double u = im[i] + theta * rof_div(pin, y, x, W);
+  double gx = 0.0, gy = 0.0;
+  if (x < W - 1) gx = (im[i + 1] + theta * rof_div(pin, y, x + 1, W)) - u;
+  if (y < H - 1) gy = (im[i + W] + theta * rof_div(pin, y + 1, x, W)) - u;
+  double2 p = pin[i];
+  p.x = p.x + delta * gx;
+  p.y = p.y + delta * gy;
+  double nrm = fmax(sqrt(p.x * p.x + p.y * p.y), 1.0);
+  p.x = p.x / nrm;
+  p.y = p.y / nrm;
+  pout[i] = p;
+}
+
+__global__ void rof_finish_kernel(const double *__restrict__ im, const double2 *__restrict__ p,
+                                  double *__restrict__ out, int H, int W, double theta, double alp) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  long long off = (long long)blockIdx.z * H * W;
+  long long i = (long long)y * W + x;
+  double s = im[off + i] + theta * rof_div(p + off, y, x, W);
+  out[off + i] = im[off + i] - alp * s;
+}
+
+int k_rof_texture(b200flow_ctx *ctx, const double *img, double *out, int B, int C, int H, int W, double theta,
+                  int iters, double alp) {
+  long long HW = (long long)H * W;
+  int P = B * C;
+  double *norm;
+  double2 *pa, *pb;
+  BF_TRY(arena_alloc(ctx, &norm, (size_t)P * HW));
+  BF_TRY(arena_alloc(ctx, &pa, (size_t)P * HW));
+  BF_TRY(arena_alloc(ctx, &pb, (size_t)P * HW));
+  BF_TRY(k_minmax_scale(ctx, img, norm, B, (long long)C * HW, -1.0, 1.0));   // joint over the channels of a pair
+  BF_CUDA(ctx, cudaMemsetAsync(pa, 0, sizeof(double2) * P * HW, ctx->stream));
+  dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), P);
+  double delta = 1.0 / (4.0 * theta);
+  for (int it = 0; it < iters; ++it) {
+    BF_LAUNCH(ctx, rof_iter_kernel, grd, blk, 0, norm, pa, pb, H, W, theta, delta);
+    std::swap(pa, pb);
+  }
+  BF_LAUNCH(ctx, rof_finish_kernel, grd, blk, 0, norm, pa, (double *)pb, H, W, theta, alp);
+  BF_TRY(k_minmax_scale(ctx, (double *)pb, out, B, (long long)C * HW, 0.0, 255.0));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian pyramid level: correlate(prev, G, 'reflect') then MATLAB-convention bilinear resize
+// (pyramid.py:11-73).  One thread per OUTPUT pixel: 4 smoothed taps x ks^2 MACs.
+// ------------------------------------------------------------------------------------------------
+struct Taps { double k[81]; int ks; };
+
+__device__ __forceinline__ double smooth_at(const double *__restrict__ src, int H, int W, int y, int x, const Taps &t) {
+  int c = t.ks / 2;
+  double acc = 0.0;
+  for (int a = 0; a < t.ks; ++a) {
+    const double *row = src + (long long)reflect_idx(y + a - c, H) * W;
+    for (int b = 0; b < t.ks; ++b) acc += t.k[a * t.ks + b] * row[reflect_idx(x + b - c, W)];
+  }
+  return acc;
+}
+
+__device__ __forceinline__ double resize_coord(int o, int n_out, int n_in) {
+  double scale = (double)n_out / (double)n_in;
+  double c = ((double)o + 0.5) / scale - 0.5;
+  double hi = (double)(n_in - 1);
+  return c < 0.0 ? 0.0 : (c > hi ? hi : c);
+}
+
+__global__ void gauss_resize_kernel(const double *__restrict__ src, double *__restrict__ dst, int H, int W, int Hn,
+                                    int Wn, Taps t) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= Wn || y >= Hn) return;
+  src += (long long)blockIdx.z * H * W;
+  dst += (long long)blockIdx.z * Hn * Wn;
+  double r = resize_coord(y, Hn, H), c = resize_coord(x, Wn, W);
+  int r0 = (int)floor(r), c0 = (int)floor(c);
+  double tr = r - (double)r0, tc = c - (double)c0;
+  int r1 = min(r0 + 1, H - 1), c1 = min(c0 + 1, W - 1);
+  double z00 = smooth_at(src, H, W, r0, c0, t), z01 = smooth_at(src, H, W, r0, c1, t);
+  double z10 = smooth_at(src, H, W, r1, c0, t), z11 = smooth_at(src, H, W, r1, c1, t);
+  dst[(long long)y * Wn + x] = (1.0 - tr) * ((1.0 - tc) * z00 + tc * z01) + tr * ((1.0 - tc) * z10 + tc * z11);
+}
+
+int k_gauss_resize(b200flow_ctx *ctx, const double *src, double *dst, int P, int H, int W, int Hn, int Wn,
+                   const double *taps, int ks) {
+  if (ks > 9 || ks < 1 || (ks & 1) == 0)
+    return set_err(ctx, B200FLOW_EINVAL, "pyramid smoothing kernel size %d unsupported (odd, <= 9)", ks);
+  Taps t;
+  t.ks = ks;
+  for (int i = 0; i < ks * ks; ++i) t.k[i] = taps[i];
+  dim3 blk(32, 8), grd((unsigned)cdiv(Wn, 32), (unsigned)cdiv(Hn, 8), P);
+  BF_LAUNCH(ctx, gauss_resize_kernel, grd, blk, 0, src, dst, H, W, Hn, Wn, t);
+  return 0;
+}
+
+// base.py:185-188 + image_processing.py:29-49
+void gaussian_taps(double spacing, double *taps, int *ks_out) {
+  double sigma = std::sqrt(spacing) / std::sqrt(2.0);
+  int ks = 2 * (int)std::nearbyint(1.5 * sigma) + 1;   // Python round() = half-to-even = nearbyint in default mode
+  if (ks > 9) ks = 9;                                     // spacing <= 8 gives ks <= 7
+  double r = (ks - 1) / 2.0, mx = 0.0, sum = 0.0;
+  for (int a = 0; a < ks; ++a)
+    for (int b = 0; b < ks; ++b) {
+      double y = a - r, x = b - r;
+      double v = std::exp(-(x * x + y * y) / (2 * sigma * sigma));
+      taps[a * ks + b] = v;
+      mx = std::max(mx, v);
+    }
+  for (int i = 0; i < ks * ks; ++i) {
+    if (taps[i] < 2.220446049250313e-16 * mx) taps[i] = 0.0;
+    sum += taps[i];
+  }
+  if (sum != 0.0)
+    for (int i = 0; i < ks * ks; ++i) taps[i] /= sum;
+  *ks_out = ks;
+}
+
+int level_size(int n, double ratio) {
+  int v = (int)std::floor(n * ratio + 0.5);
+  return v < 1 ? 1 : v;
+}
+
+int auto_levels(int H, int W, double spacing) {
+  int m = H < W ? H : W;
+  return 1 + (int)std::floor(std::log(m / 16.0) / std::log(spacing));
+}
+
+// ------------------------------------------------------------------------------------------------
+// resample_flow (warping.py:6-45): bilinear resize, both components times the HEIGHT ratio
+// ------------------------------------------------------------------------------------------------
+__global__ void resample_flow_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, int h, int w, int H,
+                                     int W) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  in += (long long)blockIdx.z * h * w;
+  out += (long long)blockIdx.z * H * W;
+  double2 res;
+  if (h == H && w == W) {
+    res = in[(long long)y * w + x];
+  } else {
+    double r = resize_coord(y, H, h), c = resize_coord(x, W, w);
+    int r0 = (int)floor(r), c0 = (int)floor(c);
+    double tr = r - (double)r0, tc = c - (double)c0;
+    int r1 = min(r0 + 1, h - 1), c1 = min(c0 + 1, w - 1);
+    double2 z00 = in[(long long)r0 * w + c0], z01 = in[(long long)r0 * w + c1];
+    double2 z10 = in[(long long)r1 * w + c0], z11 = in[(long long)r1 * w + c1];
+    double ratio = (double)H / (double)h;
+    res.x = ((1.0 - tr) * ((1.0 - tc) * z00.x + tc * z01.x) + tr * ((1.0 - tc) * z10.x + tc * z11.x)) * ratio;
+    res.y = ((1.0 - tr) * ((1.0 - tc) * z00.y + tc * z01.y) + tr * ((1.0 - tc) * z10.y + tc * z11.y)) * ratio;
+  }
+  out[(long long)y * W + x] = res;
+}
+
+int k_resample_flow(b200flow_ctx *ctx, const double2 *in, double2 *out, int B, int h, int w, int H, int W) {
+  dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
+  BF_LAUNCH(ctx, resample_flow_kernel, grd, blk, 0, in, out, h, w, H, W);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// colour conversion (interface.py:74-141)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gray_from_q(double r, double g, double b) {
+  // ((0.2989 R + 0.5870 G) + 0.1140 B), then round half up -- same association as the NumPy expression
+  double s = 0.2989 * r + 0.5870 * g;
+  s = s + 0.1140 * b;
+  return floor(s + 0.5);
+}
+
+__device__ __forceinline__ double quant8(double v) {   // clip(floor(v + .5), 0, 255) then uint8 cast
+  double q = floor(v + 0.5);
+  return q < 0.0 ? 0.0 : (q > 255.0 ? 255.0 : q);
+}
+
+__device__ __forceinline__ void lab_from_rgb01(double r, double g, double b, double &L, double &A, double &Bb) {
+  // XYZ = MAT @ RGB: each row is a 3-term dot product accumulated left to right
+  double X = (0.412453 * r + 0.357580 * g) + 0.180423 * b;
+  double Y = (0.212671 * r + 0.715160 * g) + 0.072169 * b;
+  double Z = (0.019334 * r + 0.119193 * g) + 0.950227 * b;
+  X = X / 0.950456;
+  Z = Z / 1.088754;
+  const double T = 0.008856, third = 1.0 / 3.0, lin = 16.0 / 116.0;
+  double Y3 = pow(Y, third);
+  double fX = X > T ? pow(X, third) : 7.787 * X + lin;
+  double fY = Y > T ? Y3 : 7.787 * Y + lin;
+  double fZ = Z > T ? pow(Z, third) : 7.787 * Z + lin;
+  L = Y > T ? 116.0 * Y3 - 16.0 : 903.3 * Y;
+  A = 500.0 * (fX - fY);
+  Bb = 200.0 * (fY - fZ);
+}
+
+__global__ void rgb8_max_kernel(const unsigned char *__restrict__ rgb, long long n_per_item, int *__restrict__ mx) {
+  const unsigned char *p = rgb + (long long)blockIdx.y * n_per_item;
+  int m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_per_item; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, (int)p[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&mx[blockIdx.y], m);
+}
+
+__global__ void rgb8_convert_kernel(const unsigned char *__restrict__ rgb1, const unsigned char *__restrict__ rgb2,
+                                    long long HW, double *__restrict__ gray, double *__restrict__ lab,
+                                    const int *__restrict__ mx) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  int b = blockIdx.y;
+  const unsigned char *a = rgb1 + ((long long)b * HW + i) * 3;
+  const unsigned char *c = rgb2 + ((long long)b * HW + i) * 3;
+  gray[((long long)b * 2 + 0) * HW + i] = gray_from_q(a[0], a[1], a[2]);
+  gray[((long long)b * 2 + 1) * HW + i] = gray_from_q(c[0], c[1], c[2]);
+  if (lab) {
+    double r = a[0], g = a[1], bl = a[2];
+    if (mx[b] > 1) { r = r / 255.0; g = g / 255.0; bl = bl / 255.0; }
+    double L, A, Bb;
+    lab_from_rgb01(r, g, bl, L, A, Bb);
+    lab[((long long)b * 3 + 0) * HW + i] = L;
+    lab[((long long)b * 3 + 1) * HW + i] = A;
+    lab[((long long)b * 3 + 2) * HW + i] = Bb;
+  }
+}
+
+int k_rgb8_to_gray_lab(b200flow_ctx *ctx, const unsigned char *rgb1, const unsigned char *rgb2, int B, long long HW,
+                       double *gray, double *lab) {
+  int *mx;
+  BF_TRY(arena_alloc(ctx, &mx, (size_t)B));
+  BF_CUDA(ctx, cudaMemsetAsync(mx, 0, sizeof(int) * B, ctx->stream));
+  if (lab) BF_LAUNCH(ctx, rgb8_max_kernel, dim3(32, B), 256, 0, rgb1, HW * 3, mx);
+  BF_LAUNCH(ctx, rgb8_convert_kernel, dim3((unsigned)cdiv(HW, 256), B), 256, 0, rgb1, rgb2, HW, gray, lab, mx);
+  return 0;
+}
+
+__global__ void rgbf_gray_kernel(const double *__restrict__ rgb, long long HW, double *__restrict__ gray) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  gray[i] = gray_from_q(quant8(rgb[i * 3]), quant8(rgb[i * 3 + 1]), quant8(rgb[i * 3 + 2]));
+}
+
+__global__ void rgbf_lab_kernel(const double *__restrict__ rgb, long long HW, double *__restrict__ lab,
+                                const double2 *__restrict__ mm) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  double r = rgb[i * 3], g = rgb[i * 3 + 1], b = rgb[i * 3 + 2];
+  if (mm[0].y > 1.0) { r = r / 255.0; g = g / 255.0; b = b / 255.0; }   // any channel max > 1 (interface.py:103-106)
+  double L, A, Bb;
+  lab_from_rgb01(r, g, b, L, A, Bb);
+  lab[i] = L;
+  lab[HW + i] = A;
+  lab[2 * HW + i] = Bb;
+}
+
+int k_rgbf_to_gray(b200flow_ctx *ctx, const double *rgb, long long HW, double *gray) {
+  BF_LAUNCH(ctx, rgbf_gray_kernel, (unsigned)cdiv(HW, 256), 256, 0, rgb, HW, gray);
+  return 0;
+}
+
+int k_rgbf_to_lab(b200flow_ctx *ctx, const double *rgb, long long HW, double *lab) {
+  double2 *mm;
+  BF_TRY(minmax_items(ctx, rgb, 1, HW * 3, &mm));
+  BF_LAUNCH(ctx, rgbf_lab_kernel, (unsigned)cdiv(HW, 256), 256, 0, rgb, HW, lab, mm);
+  return 0;
+}
+
+}  // namespace bf

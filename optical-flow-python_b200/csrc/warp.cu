@@ -1,0 +1,432 @@
+// warp.cu -- kernel groups (2)+(3): per-level derivative planes, cubic B-spline prefilter, and the fused
+// warp + Ix/Iy/It + robust IRLS weights + five-point-system assembly kernel.
+// Replaces derivatives.py:27-296 (partial_deriv, interp2_bicubic), penalties.py (deriv_over_x, all 10
+// penalties) and flow_operator (classic_nl.py:279-378, ba.py:208-302, hs.py:144-203) of the reference.
+#include "kernels.cuh"
+
+namespace bf {
+
+// ------------------------------------------------------------------------------------------------
+// robust penalties, d_type 0/1/2 (penalties.py:18-345; App. B of SURVEY.md)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pen_weight(const b200flow_penalty &pn, double x) {   // rho'(x)/x
+  double s2 = pn.p0 * pn.p0;
+  switch (pn.kind) {
+    case 0: return 2.0 / s2;
+    case 1: return 2.0 / (2.0 * s2 + x * x);
+    case 2: { double q = x / s2; return 1.0 / (s2 * sqrt(1.0 + q * q)); }
+    case 3: return 2.0 * pn.p1 * pow(s2 + x * x, pn.p1 - 1.0);
+    case 4: { double d = s2 + x * x; return 2.0 * s2 / (d * d); }
+    case 5: { double ax = fabs(x); return ax <= s2 ? 2.0 : 2.0 * s2 / fmax(ax, 1e-30); }
+    case 6: { double om = 1.0 - (x * x) / s2; return fabs(x) <= pn.p0 ? 2.0 * (om * om) / s2 : 0.0; }
+    case 7: return 1.0 / s2;
+    case 8:
+    case 9: return (pn.p0 + 1.0) / (pn.p1 * pn.p1 * pn.p0 + x * x);
+  }
+  return 0.0;
+}
+
+__device__ double pen_eval(const b200flow_penalty &pn, int d_type, double x, double tdist_const) {
+  if (d_type == 2) return pen_weight(pn, x);
+  double s2 = pn.p0 * pn.p0;
+  switch (pn.kind) {
+    case 0: return d_type == 0 ? x * x / s2 : 2.0 * x / s2;
+    case 1: return d_type == 0 ? log(1.0 + x * x / (2.0 * s2)) : 2.0 * x / (2.0 * s2 + x * x);
+    case 2: { double q = x / s2; double r = sqrt(1.0 + q * q); return d_type == 0 ? s2 * r : x / (s2 * r); }
+    case 3: { double base = s2 + x * x;
+              return d_type == 0 ? pow(base, pn.p1) : 2.0 * pn.p1 * x * pow(base, pn.p1 - 1.0); }
+    case 4: { double d = s2 + x * x; return d_type == 0 ? x * x / d : 2.0 * s2 * x / (d * d); }
+    case 5: { double ax = fabs(x); bool in = ax <= s2;
+              if (d_type == 0) return in ? x * x : 2.0 * s2 * ax - s2 * s2;
+              return in ? 2.0 * x : 2.0 * s2 * (x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0)); }
+    case 6: { double om = 1.0 - (x * x) / s2; bool in = fabs(x) <= pn.p0;
+              if (d_type == 0) return in ? (1.0 / 3.0) * (1.0 - om * om * om) : 1.0 / 3.0;
+              return in ? 2.0 * x * (om * om) / s2 : 0.0; }
+    case 7: { double q = x / pn.p0;
+              return d_type == 0 ? 0.5 * log(2.0 * 3.141592653589793) + log(pn.p0) + 0.5 * (q * q) : x / s2; }
+    case 8:
+    case 9: { double s2r = pn.p1 * pn.p1 * pn.p0;
+              if (d_type == 0) return (pn.p0 + 1.0) / 2.0 * log(1.0 + x * x / s2r) + tdist_const;
+              return (pn.p0 + 1.0) * x / (s2r + x * x); }
+  }
+  return 0.0;
+}
+
+__global__ void robust_eval_kernel(b200flow_penalty pn, int d_type, const double *__restrict__ x, long long n,
+                                   double *__restrict__ y, double tdist_const) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = pen_eval(pn, d_type, x[i], tdist_const);
+}
+
+int k_robust_eval(b200flow_ctx *ctx, b200flow_penalty pen, int d_type, const double *x, long long n, double *y) {
+  if (pen.kind < 0 || pen.kind > 9) return set_err(ctx, B200FLOW_EINVAL, "Unknown penalty kind %d", pen.kind);
+  if (d_type < 0 || d_type > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown d_type: %d", d_type);
+  double c = 0.0;
+  if (pen.kind == 8)   // tdist normalisation constant is a host-side scalar (penalties.py:304-306)
+    c = std::lgamma(pen.p0 / 2.0) - std::lgamma((pen.p0 + 1.0) / 2.0) + 0.5 * std::log(pen.p0 * 3.141592653589793) +
+        std::log(pen.p1);
+  if (n > 0) BF_LAUNCH(ctx, robust_eval_kernel, (unsigned)cdiv(n, 256), 256, 0, pen, d_type, x, n, y, c);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-level derivative planes (once per level, not per warp)
+//   I1x, I1y             5-tap correlate of frame 1, scipy 'reflect'          (derivatives.py:201-202,258-259)
+//   Hermite source       {Z, DX, DY, DXY} of frame 2, DXY = 5x5 outer(h,h)    (derivatives.py:77-86)
+//   spline source        {I2, I2x, I2y, 0}, then prefiltered in place          (derivatives.py:244-254)
+// algorithmic bytes/pixel: read 16, write 16 + 32 = 64 B
+// ------------------------------------------------------------------------------------------------
+struct Filt5 { double h[5]; };
+
+__global__ void level_prep_kernel(const double *__restrict__ im1, const double *__restrict__ im2, long long bstride,
+                                  int H, int W, int hermite, Filt5 f, double *__restrict__ I1x,
+                                  double *__restrict__ I1y, double4 *__restrict__ src2) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  long long off = (long long)blockIdx.z * H * W;
+  im1 += (long long)blockIdx.z * bstride; im2 += (long long)blockIdx.z * bstride;
+  int xs[5], ys[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { xs[k] = reflect_idx(x + k - 2, W); ys[k] = reflect_idx(y + k - 2, H); }
+  double a1x = 0.0, a1y = 0.0, a2x = 0.0, a2y = 0.0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    a1x += f.h[k] * im1[(long long)y * W + xs[k]];
+    a1y += f.h[k] * im1[(long long)ys[k] * W + x];
+    a2x += f.h[k] * im2[(long long)y * W + xs[k]];
+    a2y += f.h[k] * im2[(long long)ys[k] * W + x];
+  }
+  long long i = off + (long long)y * W + x;
+  I1x[i] = a1x;
+  I1y[i] = a1y;
+  double dxy = 0.0;
+  if (hermite) {
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        double k = f.h[a] * f.h[b];
+        if (k != 0.0) dxy += k * im2[(long long)ys[a] * W + xs[b]];
+      }
+  }
+  src2[i] = make_double4(im2[(long long)y * W + x], a2x, a2y, dxy);
+}
+
+// cubic B-spline prefilter, pole z = sqrt(3)-2, gain 6, whole-sample mirror boundary, in place on the three
+// live components of the double4 (scipy ni_splines.c apply_filter).  One thread per line.
+__device__ __forceinline__ void d4_scale(double4 &v, double s) { v.x *= s; v.y *= s; v.z *= s; }
+
+__global__ void bspline_prefilter_kernel(double4 *__restrict__ c, int H, int W, int along_x, int nlines) {
+  int line = blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= nlines) return;
+  int n, stride;
+  long long base;
+  if (along_x) {            // lines are rows: line = plane*H + y
+    n = W; stride = 1; base = (long long)line * W;
+  } else {                  // lines are columns: line = plane*W + x
+    n = H; stride = W; base = (long long)(line / W) * H * W + (line % W);
+  }
+  if (n < 2) return;
+  const double z = -0.2679491924311227064725536584941276330571947461896193719441930205;   // sqrt(3)-2
+  const double gain = (1.0 - z) * (1.0 - 1.0 / z);
+  double4 *p = c + base;
+  // pass 0: gain + causal initialisation sum  c0 = [c0 + z^(n-1) c_{n-1} + sum_{i=1}^{n-2} z^i (c_i + z^(n-1) c_{n-1-i})] / (1 - z^(2n-2))
+  double zn1 = pow(z, (double)(n - 1));
+  double4 first = p[0], last = p[(long long)(n - 1) * stride];
+  d4_scale(first, gain);
+  d4_scale(last, gain);
+  double sx = first.x + zn1 * last.x, sy = first.y + zn1 * last.y, sz = first.z + zn1 * last.z;
+  double zi = z;
+  for (int i = 1; i < n - 1; ++i) {
+    double4 a = p[(long long)i * stride], b = p[(long long)(n - 1 - i) * stride];
+    sx += zi * (a.x * gain + zn1 * (b.x * gain));
+    sy += zi * (a.y * gain + zn1 * (b.y * gain));
+    sz += zi * (a.z * gain + zn1 * (b.z * gain));
+    zi *= z;
+    if (fabs(zi) < 1e-300 && zn1 == 0.0) break;   // remaining terms are exactly negligible
+  }
+  double den = 1.0 - zn1 * zn1;
+  double4 prev = make_double4(sx / den, sy / den, sz / den, 0.0);
+  p[0] = prev;
+  // pass 1: causal recursion c_i += z c_{i-1}  (input still unscaled for i >= 1)
+  for (int i = 1; i < n; ++i) {
+    double4 v = p[(long long)i * stride];
+    v.x = v.x * gain + z * prev.x;
+    v.y = v.y * gain + z * prev.y;
+    v.z = v.z * gain + z * prev.z;
+    p[(long long)i * stride] = v;
+    prev = v;
+  }
+  // pass 2: anticausal initialisation and recursion c_i = z (c_{i+1} - c_i)
+  double4 pm = p[(long long)(n - 2) * stride];
+  double k = z / (z * z - 1.0);
+  prev.x = (z * pm.x + prev.x) * k;
+  prev.y = (z * pm.y + prev.y) * k;
+  prev.z = (z * pm.z + prev.z) * k;
+  p[(long long)(n - 1) * stride] = prev;
+  for (int i = n - 2; i >= 0; --i) {
+    double4 v = p[(long long)i * stride];
+    v.x = z * (prev.x - v.x);
+    v.y = z * (prev.y - v.y);
+    v.z = z * (prev.z - v.z);
+    p[(long long)i * stride] = v;
+    prev = v;
+  }
+}
+
+int k_level_prep(b200flow_ctx *ctx, const double *im1, const double *im2, long long bstride, int B, int H, int W,
+                 int interp, const double filt[5], double *I1x, double *I1y, double4 *src2) {
+  Filt5 f;
+  for (int i = 0; i < 5; ++i) f.h[i] = filt[i];
+  dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
+  BF_LAUNCH(ctx, level_prep_kernel, grd, blk, 0, im1, im2, bstride, H, W,
+            interp == B200FLOW_INTERP_BICUBIC ? 1 : 0, f, I1x, I1y, src2);
+  if (interp == B200FLOW_INTERP_CUBIC) {
+    // scipy spline_filter: axis 0 (columns) first, then axis 1 (rows)
+    int ncol = B * W, nrow = B * H;
+    BF_LAUNCH(ctx, bspline_prefilter_kernel, (unsigned)cdiv(ncol, 64), 64, 0, src2, H, W, 0, ncol);
+    BF_LAUNCH(ctx, bspline_prefilter_kernel, (unsigned)cdiv(nrow, 64), 64, 0, src2, H, W, 1, nrow);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp + derivatives (partial_deriv) for one pixel
+// ------------------------------------------------------------------------------------------------
+struct Deriv { double It, Ix, Iy; };
+
+// 32-byte gather element through the read-only path as two 128-bit loads (one sector)
+__device__ __forceinline__ double4 ld4(const double4 *p) {
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ void hermite_basis(double t, double &h0, double &h1, double &g0, double &g1, double &dh0,
+                                              double &dh1, double &dg0, double &dg1) {
+  double t2 = t * t, t3 = t2 * t;
+  h0 = 2.0 * t3 - 3.0 * t2 + 1.0;
+  h1 = -2.0 * t3 + 3.0 * t2;
+  g0 = t3 - 2.0 * t2 + t;
+  g1 = t3 - t2;
+  dh0 = 6.0 * t2 - 6.0 * t;
+  dh1 = -6.0 * t2 + 6.0 * t;
+  dg0 = 3.0 * t2 - 4.0 * t + 1.0;
+  dg1 = 3.0 * t2 - 2.0 * t;
+}
+
+// tensor-product cubic Hermite on the unit cell == the 16x16 bcucof/bcuint product of interp2_bicubic
+// (derivatives.py:27-145; closed form of SURVEY App. A.4b).  x1,y1 are 1-based sample coordinates.
+__device__ __forceinline__ bool warp_hermite(const double4 *__restrict__ s, int H, int W, double x1, double y1,
+                                             double &val, double &ddx, double &ddy) {
+  double flx = floor(x1), fly = floor(y1);
+  // compare in double so that huge / non-finite flows are classified out of bounds instead of overflowing int
+  bool oob = !(flx >= 1.0) || !(flx + 1.0 <= (double)W) || !(fly >= 1.0) || !(fly + 1.0 <= (double)H);
+  if (oob) { val = ddx = ddy = 0.0; return false; }
+  int fx = (int)flx, fy = (int)fly;
+  int x0 = fx - 1, xb = fx, y0 = fy - 1, yb = fy;   // 0-based corners (already inside the image)
+  double ax = x1 - flx, ay = y1 - fly;
+  double hx[2], gx[2], dhx[2], dgx[2], hy[2], gy[2], dhy[2], dgy[2];
+  hermite_basis(ax, hx[0], hx[1], gx[0], gx[1], dhx[0], dhx[1], dgx[0], dgx[1]);
+  hermite_basis(ay, hy[0], hy[1], gy[0], gy[1], dhy[0], dhy[1], dgy[0], dgy[1]);
+  val = ddx = ddy = 0.0;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      double4 c = ld4(&s[(long long)(b ? yb : y0) * W + (a ? xb : x0)]);   // {Z, DX, DY, DXY}
+      val += c.x * hx[a] * hy[b] + c.y * gx[a] * hy[b] + c.z * hx[a] * gy[b] + c.w * gx[a] * gy[b];
+      ddx += c.x * dhx[a] * hy[b] + c.y * dgx[a] * hy[b] + c.z * dhx[a] * gy[b] + c.w * dgx[a] * gy[b];
+      ddy += c.x * hx[a] * dhy[b] + c.y * gx[a] * dhy[b] + c.z * hx[a] * dgy[b] + c.w * gx[a] * dgy[b];
+    }
+  return true;
+}
+
+// scipy map_coordinates(order=3 | 1, mode='constant', cval=nan) on {I2, I2x, I2y}; x0,y0 0-based
+__device__ __forceinline__ void warp_spline(const double4 *__restrict__ s, int H, int W, double x0, double y0,
+                                            int order, double &val, double &vx, double &vy) {
+  double flx = floor(x0), fly = floor(y0);
+  int fx = (int)flx, fy = (int)fly;
+  double tx = x0 - flx, ty = y0 - fly;
+  val = vx = vy = 0.0;
+  if (order == 3) {
+    double wx[4], wy[4];
+    {
+      double z = 1.0 - tx;
+      wx[1] = (tx * tx * (tx - 2.0) * 3.0 + 4.0) / 6.0;
+      wx[2] = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
+      wx[0] = z * z * z / 6.0;
+      wx[3] = 1.0 - wx[0] - wx[1] - wx[2];
+      z = 1.0 - ty;
+      wy[1] = (ty * ty * (ty - 2.0) * 3.0 + 4.0) / 6.0;
+      wy[2] = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
+      wy[0] = z * z * z / 6.0;
+      wy[3] = 1.0 - wy[0] - wy[1] - wy[2];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double4 *row = s + (long long)mirror_idx(fy + a - 1, H) * W;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        double4 c = ld4(&row[mirror_idx(fx + b - 1, W)]);
+        double w = wy[a] * wx[b];
+        val += c.x * w;
+        vx += c.y * w;
+        vy += c.z * w;
+      }
+    }
+  } else {
+    int x1 = mirror_idx(fx + 1, W), y1 = mirror_idx(fy + 1, H);
+    double4 c00 = ld4(&s[(long long)fy * W + fx]), c01 = ld4(&s[(long long)fy * W + x1]);
+    double4 c10 = ld4(&s[(long long)y1 * W + fx]), c11 = ld4(&s[(long long)y1 * W + x1]);
+    val = (1.0 - ty) * ((1.0 - tx) * c00.x + tx * c01.x) + ty * ((1.0 - tx) * c10.x + tx * c11.x);
+    vx = (1.0 - ty) * ((1.0 - tx) * c00.y + tx * c01.y) + ty * ((1.0 - tx) * c10.y + tx * c11.y);
+    vy = (1.0 - ty) * ((1.0 - tx) * c00.z + tx * c01.z) + ty * ((1.0 - tx) * c10.z + tx * c11.z);
+  }
+}
+
+__device__ __forceinline__ Deriv pixel_deriv(const double *__restrict__ im1, const double *__restrict__ I1x,
+                                             const double *__restrict__ I1y, const double4 *__restrict__ src2,
+                                             int H, int W, int x, int y, double2 f, int interp, double blend) {
+  long long i = (long long)y * W + x;
+  double x2 = (double)(x + 1) + f.x, y2 = (double)(y + 1) + f.y;   // 1-based, as the reference's meshgrid
+  double val, wx, wy;
+  bool ok;
+  if (interp == B200FLOW_INTERP_BICUBIC) {
+    ok = warp_hermite(src2, H, W, x2, y2, val, wx, wy);
+  } else {
+    ok = !(x2 > (double)W) && !(x2 < 1.0) && !(y2 > (double)H) && !(y2 < 1.0) && x2 == x2 && y2 == y2;
+    if (ok) warp_spline(src2, H, W, x2 - 1.0, y2 - 1.0, interp == B200FLOW_INTERP_CUBIC ? 3 : 1, val, wx, wy);
+  }
+  Deriv d;
+  if (!ok) { d.It = d.Ix = d.Iy = 0.0; return d; }
+  d.It = val - im1[i];
+  d.Ix = blend * wx + (1.0 - blend) * I1x[i];
+  d.Iy = blend * wy + (1.0 - blend) * I1y[i];
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IRLS weights + system assembly for one pixel (flow_operator + GNC blend)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double blended_edge(const PenaltySet &ps, const b200flow_penalty &rob,
+                                               const b200flow_penalty &qua, double delta) {
+  if (ps.hs) return ps.hs_w;
+  double w = 0.0;
+  if (ps.alpha > 0.0) w = w + ps.alpha * (ps.lambda_q * pen_weight(qua, delta));
+  if (ps.alpha < 1.0) w = w + (1.0 - ps.alpha) * (ps.lambda * pen_weight(rob, delta));
+  return w;
+}
+
+__device__ __forceinline__ double blended_data(const PenaltySet &ps, double it_lin) {
+  if (ps.hs) return ps.hs_d;
+  double d = 0.0;
+  if (ps.alpha > 0.0) d = d + ps.alpha * pen_weight(ps.qua_d, it_lin);
+  if (ps.alpha < 1.0) d = d + (1.0 - ps.alpha) * pen_weight(ps.rho_d, it_lin);
+  return d;
+}
+
+__device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const double2 *__restrict__ uv,
+                                               const double2 *__restrict__ duv, int H, int W, int x, int y, Deriv dv,
+                                               const LinSys &sys, long long gi) {
+  long long i = (long long)y * W + x;
+  double2 c0 = uv[i];                                       // uv (for the rhs Laplacian)
+  double2 dc = duv ? duv[i] : make_double2(0.0, 0.0);
+  double2 c = make_double2(c0.x + dc.x, c0.y + dc.y);       // uv + duv (for the weights)
+  double whu = 0.0, whv = 0.0, wvu = 0.0, wvv = 0.0;        // own right / down edges (stored)
+  double lu = 0.0, lv = 0.0;                                // sum_q w_pq (uv[p] - uv[q])
+  auto nb = [&](long long j, double2 &n0, double2 &n) {
+    n0 = uv[j];
+    double2 nd = duv ? duv[j] : make_double2(0.0, 0.0);
+    n = make_double2(n0.x + nd.x, n0.y + nd.y);
+  };
+  double2 n0, n;
+  if (x + 1 < W) {   // right: delta = f[x+1] - f[x]
+    nb(i + 1, n0, n);
+    whu = blended_edge(ps, ps.rho_su[0], ps.qua_su[0], n.x - c.x);
+    whv = blended_edge(ps, ps.rho_sv[0], ps.qua_sv[0], n.y - c.y);
+    lu += whu * (c0.x - n0.x);
+    lv += whv * (c0.y - n0.y);
+  }
+  if (x > 0) {       // left edge belongs to pixel x-1: delta = f[x] - f[x-1]
+    nb(i - 1, n0, n);
+    double wu = blended_edge(ps, ps.rho_su[0], ps.qua_su[0], c.x - n.x);
+    double wv = blended_edge(ps, ps.rho_sv[0], ps.qua_sv[0], c.y - n.y);
+    lu += wu * (c0.x - n0.x);
+    lv += wv * (c0.y - n0.y);
+  }
+  if (y + 1 < H) {   // down
+    nb(i + W, n0, n);
+    wvu = blended_edge(ps, ps.rho_su[1], ps.qua_su[1], n.x - c.x);
+    wvv = blended_edge(ps, ps.rho_sv[1], ps.qua_sv[1], n.y - c.y);
+    lu += wvu * (c0.x - n0.x);
+    lv += wvv * (c0.y - n0.y);
+  }
+  if (y > 0) {       // up
+    nb(i - W, n0, n);
+    double wu = blended_edge(ps, ps.rho_su[1], ps.qua_su[1], c.x - n.x);
+    double wv = blended_edge(ps, ps.rho_sv[1], ps.qua_sv[1], c.y - n.y);
+    lu += wu * (c0.x - n0.x);
+    lv += wv * (c0.y - n0.y);
+  }
+  double it_lin = dv.It + dv.Ix * dc.x + dv.Iy * dc.y;
+  double d = blended_data(ps, it_lin);
+  sys.D[gi] = make_double2(d * dv.Ix * dv.Ix, d * dv.Iy * dv.Iy);
+  sys.a12[gi] = d * dv.Ix * dv.Iy;
+  sys.WH[gi] = make_double2(whu, whv);
+  sys.WV[gi] = make_double2(wvu, wvv);
+  sys.rhs[gi] = make_double2(-lu - d * it_lin * dv.Ix, -lv - d * it_lin * dv.Iy);
+}
+
+// algorithmic bytes per pixel: read uv 16 + im1,I1x,I1y 24 + gathered source 32,
+// write D 16 + a12 8 + WH 16 + WV 16 + rhs 16  = 144 B
+__global__ void __launch_bounds__(256) warp_assemble_kernel(const double *__restrict__ im1, long long bstride,
+                                     const double *__restrict__ I1x,
+                                     const double *__restrict__ I1y, const double4 *__restrict__ src2,
+                                     const double2 *__restrict__ uv, const double2 *__restrict__ duv, int H, int W,
+                                     int interp, double blend, PenaltySet ps, LinSys sys, double *__restrict__ It,
+                                     double *__restrict__ Ix, double *__restrict__ Iy, int do_assemble) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  long long off = (long long)blockIdx.z * H * W;
+  long long i = (long long)y * W + x;
+  Deriv dv = pixel_deriv(im1 + (long long)blockIdx.z * bstride, I1x + off, I1y + off, src2 + off, H, W, x, y,
+                         uv[off + i], interp, blend);
+  if (It) { It[off + i] = dv.It; Ix[off + i] = dv.Ix; Iy[off + i] = dv.Iy; }
+  if (do_assemble) assemble_pixel(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, dv, sys, off + i);
+}
+
+__global__ void __launch_bounds__(256) assemble_from_deriv_kernel(const double *__restrict__ It, const double *__restrict__ Ix,
+                                           const double *__restrict__ Iy, const double2 *__restrict__ uv,
+                                           const double2 *__restrict__ duv, int H, int W, PenaltySet ps, LinSys sys) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  long long off = (long long)blockIdx.z * H * W;
+  long long i = (long long)y * W + x;
+  Deriv dv;
+  dv.It = It[off + i]; dv.Ix = Ix[off + i]; dv.Iy = Iy[off + i];
+  assemble_pixel(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, dv, sys, off + i);
+}
+
+int k_warp_assemble(b200flow_ctx *ctx, const double *im1, long long bstride, const double *I1x, const double *I1y,
+                    const double4 *src2, const double2 *uv, const double2 *duv, int B, int H, int W, int interp, double blend,
+                    const PenaltySet &ps, LinSys sys, double *It, double *Ix, double *Iy) {
+  if (interp < 0 || interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", interp);
+  dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
+  int do_assemble = sys.D != nullptr;
+  BF_LAUNCH(ctx, warp_assemble_kernel, grd, blk, 0, im1, bstride, I1x, I1y, src2, uv, duv, H, W, interp, blend, ps,
+            sys, It, Ix, Iy, do_assemble);
+  return 0;
+}
+
+int k_assemble_from_deriv(b200flow_ctx *ctx, const double *It, const double *Ix, const double *Iy, const double2 *uv,
+                          const double2 *duv, int B, int H, int W, const PenaltySet &ps, LinSys sys) {
+  dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
+  BF_LAUNCH(ctx, assemble_from_deriv_kernel, grd, blk, 0, It, Ix, Iy, uv, duv, H, W, ps, sys);
+  return 0;
+}
+
+}  // namespace bf

@@ -1,0 +1,45 @@
+"""Middlebury .flo files (host I/O edge of the path; reference: io/flo_io.py).
+
+Layout: float32 tag 202021.25, int32 width, int32 height, then height*width*(u,v) float32, row-major."""
+import os
+
+import numpy as np
+
+TAG_FLOAT = 202021.25
+
+
+def read_flo(filename):
+    with open(filename, 'rb') as f:
+        head = np.frombuffer(f.read(12), dtype=[('tag', '<f4'), ('w', '<i4'), ('h', '<i4')])
+        if head.size != 1 or head['tag'][0] != np.float32(TAG_FLOAT):
+            tag = head['tag'][0] if head.size else None
+            raise ValueError(f'Invalid .flo file tag: {tag} (expected {TAG_FLOAT})')
+        w, h = int(head['w'][0]), int(head['h'][0])
+        data = np.fromfile(f, '<f4', count=2 * w * h)
+    return data.reshape(h, w, 2)
+
+
+def write_flo(flow, filename):
+    flow = np.asarray(flow, dtype=np.float32)
+    if flow.ndim != 3 or flow.shape[2] != 2:
+        raise ValueError(f"Flow must be (H, W, 2) array, got shape {flow.shape}")
+    h, w = flow.shape[:2]
+    with open(filename, 'wb') as f:
+        f.write(np.float32(TAG_FLOAT).tobytes())
+        f.write(np.array([w, h], dtype='<i4').tobytes())
+        f.write(np.ascontiguousarray(flow, dtype='<f4').tobytes())
+
+
+def read_flow_file(seq_name, i_seq, data_dir=None):
+    """(im1, im2, tu, tv) of a Middlebury sequence under data_dir/other-data and data_dir/other-gt-flow."""
+    from PIL import Image
+    if data_dir is None:
+        data_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'data')
+    base = os.path.join(data_dir, 'other-data', seq_name)
+    im1 = np.array(Image.open(os.path.join(base, f'frame{i_seq:02d}.png'))).astype(np.float64)
+    im2 = np.array(Image.open(os.path.join(base, f'frame{i_seq + 1:02d}.png'))).astype(np.float64)
+    gt = os.path.join(data_dir, 'other-gt-flow', seq_name, f'flow{i_seq:02d}.flo')
+    if os.path.exists(gt):
+        fl = read_flo(gt)
+        return im1, im2, fl[:, :, 0], fl[:, :, 1]
+    return im1, im2, None, None

@@ -1,0 +1,31 @@
+"""Warping + spatio-temporal derivatives (reference: utils/derivatives.py:148-296)."""
+import ctypes as C
+
+import numpy as np
+
+from optical_flow import _lib
+
+INTERP_CODES = {'bi-cubic': 0, 'cubic': 1, 'bi-linear': 2}
+
+
+def partial_deriv(images, uv, interp_method='cubic', deriv_filter=None, blend=0.5):
+    """It, Ix, Iy of a gray frame pair (H,W,2) warped by uv.  'bi-cubic' = Hermite bicubic with analytic
+    derivatives, 'cubic' = scipy-compatible cubic B-spline, 'bi-linear'."""
+    if interp_method not in INTERP_CODES:
+        raise ValueError(f"Unknown interpolation method: {interp_method}")
+    images = _lib.f64(images)
+    uv = _lib.f64(uv)
+    if images.ndim != 3 or images.shape[2] != 2:
+        raise NotImplementedError("multi-channel colour data term (images with 2C channels, C > 1) is not built yet "
+                                  "(SURVEY.md section 8f rank 1)")
+    if deriv_filter is None:
+        deriv_filter = np.array([1, -8, 0, 8, -1]) / 12.0
+    h = _lib.f64(deriv_filter).reshape(-1)
+    if h.size != 5:
+        raise ValueError("deriv_filter must have 5 taps")
+    H, W = images.shape[:2]
+    It, Ix, Iy = np.empty((H, W)), np.empty((H, W)), np.empty((H, W))
+    _lib.default_context().call("b200flow_partial_deriv", _lib.ptr(images), _lib.ptr(uv), H, W, INTERP_CODES[interp_method],
+                                h.ctypes.data_as(C.POINTER(C.c_double)), float(blend), _lib.ptr(It), _lib.ptr(Ix),
+                                _lib.ptr(Iy))
+    return It, Ix, Iy

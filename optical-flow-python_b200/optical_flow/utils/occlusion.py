@@ -1,0 +1,16 @@
+"""Occlusion confidence from flow divergence and brightness constancy (reference: utils/occlusion.py:6-56)."""
+import numpy as np
+
+from optical_flow import _lib
+
+
+def detect_occlusion(uv, images, sigma_d=0.3, sigma_i=20.0):
+    uv = _lib.f64(uv)
+    images = _lib.f64(images)
+    if images.ndim != 3 or images.shape[2] != 2:
+        raise NotImplementedError("multi-channel images are not built yet (SURVEY.md section 8f rank 1)")
+    H, W = uv.shape[:2]
+    occ = np.empty((H, W))
+    _lib.default_context().call("b200flow_detect_occlusion", _lib.ptr(uv), _lib.ptr(images), H, W, float(sigma_d),
+                                float(sigma_i), _lib.ptr(occ))
+    return occ
