@@ -216,92 +216,136 @@ int k_sub(b200flow_ctx *ctx, const double2 *a, const double2 *b, double2 *out, l
 
 // ------------------------------------------------------------------------------------------------
 // colour/occlusion weighted median over a (2 hsz+1)^2 window (weighted_median.py:24-112)
-//   one WARP per output pixel; the window's n samples live NPL per lane in registers; two key/index
-//   bitonic sorts (u, v) with warp shuffles; ordered prefix sum of the weights; first rank whose
-//   cumulative weight reaches total/2.  Tile of colour / occ / flow staged in shared memory with the
-//   NumPy 'reflect' (mirror, no edge repeat) boundary.  Compute-bound: ~2 x 36 bitonic stages of 256 keys.
+//   one WARP per output pixel; the window's n samples (u, v, weight) live NPL per lane in registers.
+//   The reference sorts the window and walks the cumulative weights; the value it returns is
+//       t* = min { x_k : S(x_k) >= total/2 },   S(t) = sum of the weights of the samples <= t,
+//   which is found here WITHOUT sorting, by bisection on the sample values: keep an element-valued bracket
+//   [lo, hi] with S(hi) >= total/2 and S(x) < total/2 for every sample x < lo; evaluate S at the midpoint
+//   together with the largest sample <= pivot and the smallest sample > pivot (one pass over the lane's
+//   registers + three warp reductions) and snap the bracket to those samples.  The bracket shrinks by at
+//   least one distinct sample per step and typically halves (~8-10 steps for 225 samples); u and v are
+//   advanced together for instruction-level parallelism.  The result is always one of the window's samples.
+//   Tile of colour / occ / flow staged in shared memory with the NumPy 'reflect' (mirror, no edge repeat)
+//   boundary.  Compute-bound (fp64 compare/add/min/max + shuffles), ~64 B/pixel of HBM traffic.
 // ------------------------------------------------------------------------------------------------
 constexpr int WM_TW = 16, WM_TH = 8, WM_WARPS = 8;
 
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double wmin(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// fp64 exp kept out of line: it is evaluated NPL times per pixel and inlining it NPL-fold blows the instruction cache
+__device__ __noinline__ double exp_noinline(double x) { return exp(x); }
+
+// largest double strictly below a finite x
+__device__ __forceinline__ double next_below(double x) {
+  long long b = __double_as_longlong(x);
+  if (x > 0.0) return __longlong_as_double(b - 1);
+  if (x < 0.0) return __longlong_as_double(b + 1);
+  return -4.9406564584124654e-324;
+}
+
+// Weighted median of the NPL x 32 samples x[] with weights w[] held in the warp's registers (all lanes return it).
+//   t* = min { x_k : S(x_k) >= half },  S(t) = sum of w_k over x_k <= t.
+// "cheap" steps bisect the VALUE range (L, R] using only S(p) and the count n(p) (one fp64 shuffle reduction + one
+// integer REDUX); whenever a step separates nothing (ties / clustered samples) or at most two samples are left, a
+// "snap" pass tightens the bracket to the extreme samples inside it, which also resolves ties exactly.
 template <int NPL>
-__device__ __forceinline__ void bitonic_sort_warp(double (&key)[NPL], int (&idx)[NPL], int lane) {
+__device__ __forceinline__ double weighted_select(const double (&x)[NPL], const double (&w)[NPL], double half) {
+  double lo = x[0], hi = x[0];
 #pragma unroll
-  for (int k = 2; k <= 32 * NPL; k <<= 1) {
+  for (int k = 1; k < NPL; ++k) { lo = x[k] < lo ? x[k] : lo; hi = x[k] > hi ? x[k] : hi; }
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= NPL) {                       // partner element lives in lane ^ (j / NPL), same register slot
-        const int lj = j / NPL;
-        const bool lower = (lane & lj) == 0;
-        const bool asc = ((lane * NPL) & k) == 0;
-        const bool want_min = lower == asc;
+  for (int o = 16; o > 0; o >>= 1) {
+    double t0 = __shfl_xor_sync(0xffffffffu, lo, o), t1 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = t0 < lo ? t0 : lo; hi = t1 > hi ? t1 : hi;
+  }
+  if (!(lo < hi)) return hi;
+  double L = next_below(lo), R = hi;       // open-closed value bracket: S(L) < half <= S(R)
+  int nL = 0, nR = 32 * NPL;               // samples <= L, <= R
+  while (true) {
+    bool snap = nR - nL <= 2;
+    if (!snap) {
+      double p = 0.5 * (L + R);
+      if (!(p > L && p < R)) snap = true;
+      else {
+        double s = 0.0;
+        int c = 0;
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) {
-          double pk = __shfl_xor_sync(0xffffffffu, key[r], lj);
-          int pi = __shfl_xor_sync(0xffffffffu, idx[r], lj);
-          bool take = want_min ? (pk < key[r]) : (pk > key[r]);
-          key[r] = take ? pk : key[r];
-          idx[r] = take ? pi : idx[r];
-        }
-      } else {                              // both elements in this lane's registers
+        for (int k = 0; k < NPL; ++k)
+          if (x[k] <= p) { s += w[k]; c++; }
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) {
-          if ((r & j) == 0) {
-            const int r2 = r | j;
-            const bool asc = (((lane * NPL + r) & k) == 0);
-            bool sw = asc ? (key[r] > key[r2]) : (key[r] < key[r2]);
-            double ka = key[r], kb = key[r2];
-            int ia = idx[r], ib = idx[r2];
-            key[r] = sw ? kb : ka; key[r2] = sw ? ka : kb;
-            idx[r] = sw ? ib : ia; idx[r2] = sw ? ia : ib;
-          }
-        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (s >= half) { snap = c == nR; R = p; nR = c; }
+        else { snap = c == nL; L = p; nL = c; }
       }
     }
+    if (snap) {
+      // lo = smallest sample > L, hi = largest sample <= R  (both exist: the bracket holds weight)
+      double a = hi, b = lo;
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        const double xk = x[k];
+        if (xk > L) a = xk < a ? xk : a;
+        if (xk <= R) b = xk > b ? xk : b;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double t0 = __shfl_xor_sync(0xffffffffu, a, o), t1 = __shfl_xor_sync(0xffffffffu, b, o);
+        a = t0 < a ? t0 : a; b = t1 > b ? t1 : b;
+      }
+      lo = a; hi = b;
+      if (!(lo < hi)) return hi;
+      if (nR - nL <= 2) break;             // two distinct samples left: finish below
+      L = next_below(lo); R = hi;
+    }
   }
+  // final: sample-snapped bisection (at most a couple of steps)
+  while (lo < hi) {
+    double p = 0.5 * (lo + hi);
+    if (!(p < hi)) p = lo;
+    double s = 0.0, bl = lo, ab = hi;
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+      const double xk = x[k];
+      if (xk <= p) { s += w[k]; bl = xk > bl ? xk : bl; } else { ab = xk < ab ? xk : ab; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      double t0 = __shfl_xor_sync(0xffffffffu, bl, o), t1 = __shfl_xor_sync(0xffffffffu, ab, o);
+      bl = t0 > bl ? t0 : bl; ab = t1 < ab ? t1 : ab;
+    }
+    if (s >= half) hi = bl; else lo = ab;
+  }
+  return hi;
 }
 
-// after the sort lane L holds ranks L*NPL .. L*NPL+NPL-1; returns the weighted median (all lanes)
-template <int NPL>
-__device__ __forceinline__ double select_weighted(const double (&key)[NPL], const int (&idx)[NPL],
-                                                  const double *__restrict__ wbuf, int lane) {
-  double c[NPL];
-  double run = 0.0;
-#pragma unroll
-  for (int r = 0; r < NPL; ++r) { run += wbuf[idx[r]]; c[r] = run; }
-  double incl = run;                          // inclusive scan of lane totals, fixed order
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  double total = __shfl_sync(0xffffffffu, incl, 31);
-  double prev = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive prefix = left neighbour's inclusive value
-  double excl = lane == 0 ? 0.0 : prev;
-  double half = total / 2.0;
-  double cand = key[NPL - 1];
-  bool found = false;
-#pragma unroll
-  for (int r = NPL - 1; r >= 0; --r) {
-    if (excl + c[r] >= half) { cand = key[r]; found = true; }
-  }
-  unsigned m = __ballot_sync(0xffffffffu, found);
-  int src = m ? __ffs(m) - 1 : 31;
-  return __shfl_sync(0xffffffffu, cand, src);
-}
-
-template <int NPL>
-__global__ void __launch_bounds__(WM_WARPS * 32) wmedian_kernel(const double2 *__restrict__ cand,
-                                                               const double2 *__restrict__ base,
-                                                               const double *__restrict__ color, int C,
-                                                               const double *__restrict__ occ, int H, int W, int hsz,
-                                                               double inv2s2, double2 *__restrict__ out) {
+template <int NPL, int C>
+__global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2 *__restrict__ cand,
+                                                                  const double2 *__restrict__ base,
+                                                                  const double *__restrict__ color,
+                                                                  const double *__restrict__ occ, int H, int W, int hsz,
+                                                                  double inv2s2, double2 *__restrict__ out) {
   extern __shared__ double smem[];
   const int wsz = 2 * hsz + 1, n = wsz * wsz;
   const int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz, SN = SW * SH;
   double2 *s_uv = reinterpret_cast<double2 *>(smem);          // [SN]
   double *s_occ = smem + 2 * SN;                               // [SN]
   double *s_col = s_occ + SN;                                  // [C][SN]
-  double *s_w = s_col + (size_t)C * SN;                        // [WM_WARPS][32*NPL]
   const int b = blockIdx.z;
   const long long HW = (long long)H * W, off = (long long)b * HW;
   const int x0 = blockIdx.x * WM_TW, y0 = blockIdx.y * WM_TH;
@@ -309,47 +353,60 @@ __global__ void __launch_bounds__(WM_WARPS * 32) wmedian_kernel(const double2 *_
     int sy = t / SW, sx = t - sy * SW;
     int gy = mirror_idx(y0 + sy - hsz, H), gx = mirror_idx(x0 + sx - hsz, W);
     long long gi = (long long)gy * W + gx;
-    s_uv[t] = cand[off + gi];
+    double2 f = cand[off + gi];
+    s_uv[t] = make_double2(f.x + 0.0, f.y + 0.0);              // canonicalise -0.0
     s_occ[t] = occ[off + gi];
+#pragma unroll
     for (int c = 0; c < C; ++c) s_col[c * SN + t] = color[((long long)b * C + c) * HW + gi];
   }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *wbuf = s_w + warp * 32 * NPL;
+  // window offsets of this lane's NPL samples relative to the window's top-left corner (pixel independent)
+  int qoff[NPL];
+#pragma unroll
+  for (int k = 0; k < NPL; ++k) {
+    int e = k * 32 + lane;
+    int dy = e / wsz, dx = e - dy * wsz;
+    qoff[k] = e < n ? dy * SW + dx : -1;
+  }
+  __syncthreads();
   const int py = y0 + warp;
   if (py >= H) return;
   for (int lx = 0; lx < WM_TW; ++lx) {
     const int px = x0 + lx;
     if (px >= W) break;
-    const int ctr = (warp + hsz) * SW + lx + hsz;
-    double ku[NPL], kv[NPL];
-    int iu[NPL], iv[NPL];
+    const int org = warp * SW + lx;
+    const int ctr = org + hsz * SW + hsz;
+    double cc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) cc[c] = s_col[c * SN + ctr];
+    double x[NPL], w[NPL];
+    double tot = 0.0;
 #pragma unroll
     for (int k = 0; k < NPL; ++k) {
-      int e = k * 32 + lane;
-      double w = 0.0;
-      ku[k] = INFINITY; kv[k] = INFINITY;
-      if (e < n) {
-        int dy = e / wsz, dx = e - dy * wsz;
-        int q = (warp + dy) * SW + lx + dx;
+      w[k] = 0.0;                                  // padding slots: zero weight (and the centre value below)
+      if (qoff[k] >= 0) {
+        int q = org + qoff[k];
         double cd = 0.0;
+#pragma unroll
         for (int c = 0; c < C; ++c) {
-          double d = s_col[c * SN + q] - s_col[c * SN + ctr];
+          double d = s_col[c * SN + q] - cc[c];
           cd += d * d;
         }
-        w = fmax(exp(-cd * inv2s2) * s_occ[q], 1e-10);
-        double2 f = s_uv[q];
-        ku[k] = f.x; kv[k] = f.y;
+        double wk = exp_noinline(-cd * inv2s2) * s_occ[q];
+        w[k] = wk > 1e-10 ? wk : 1e-10;
       }
-      iu[k] = e; iv[k] = e;
-      wbuf[e] = w;
+      tot += w[k];
     }
-    __syncwarp();
-    bitonic_sort_warp<NPL>(ku, iu, lane);
-    double mu = select_weighted<NPL>(ku, iu, wbuf, lane);
-    bitonic_sort_warp<NPL>(kv, iv, lane);
-    double mv = select_weighted<NPL>(kv, iv, wbuf, lane);
-    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    const double half = tot / 2.0;
+    // padding slots repeat the centre sample with zero weight: they never change S, the minimum or the maximum
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) x[k] = s_uv[qoff[k] >= 0 ? org + qoff[k] : ctr].x;
+    const double mu = weighted_select<NPL>(x, w, half);
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) x[k] = s_uv[qoff[k] >= 0 ? org + qoff[k] : ctr].y;
+    const double mv = weighted_select<NPL>(x, w, half);
     if (lane == 0) {
       long long gi = off + (long long)py * W + px;
       if (base) {
@@ -362,17 +419,28 @@ __global__ void __launch_bounds__(WM_WARPS * 32) wmedian_kernel(const double2 *_
   }
 }
 
+template <int NPL, int C>
+static int launch_wmedian_c(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color,
+                            const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
+  int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
+  size_t smem = (size_t)SW * SH * (3 + C) * sizeof(double);
+  if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
+  BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
+  double inv2s2 = 1.0 / (2.0 * (sigma_i * sigma_i));
+  BF_LAUNCH(ctx, (wmedian_kernel<NPL, C>), grd, WM_WARPS * 32, smem, cand, base, color, occ, H, W, hsz, inv2s2, out);
+  return 0;
+}
+
 template <int NPL>
 static int launch_wmedian(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color, int C,
                           const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
-  int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
-  size_t smem = (size_t)SW * SH * (3 + C) * sizeof(double) + (size_t)WM_WARPS * 32 * NPL * sizeof(double);
-  if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
-  BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
-  double inv2s2 = 1.0 / (2.0 * (sigma_i * sigma_i));
-  BF_LAUNCH(ctx, wmedian_kernel<NPL>, grd, WM_WARPS * 32, smem, cand, base, color, C, occ, H, W, hsz, inv2s2, out);
-  return 0;
+  switch (C) {
+    case 1: return launch_wmedian_c<NPL, 1>(ctx, cand, base, color, occ, B, H, W, hsz, sigma_i, out);
+    case 2: return launch_wmedian_c<NPL, 2>(ctx, cand, base, color, occ, B, H, W, hsz, sigma_i, out);
+    case 3: return launch_wmedian_c<NPL, 3>(ctx, cand, base, color, occ, B, H, W, hsz, sigma_i, out);
+    default: return launch_wmedian_c<NPL, 4>(ctx, cand, base, color, occ, B, H, W, hsz, sigma_i, out);
+  }
 }
 
 int k_weighted_median(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color, int C,
