@@ -16,7 +16,7 @@ One JSON line on rank 0:
   value      frame-pairs/s, whole job, inputs already resident in HBM (b200flow_estimate_rgb8_dev), CUDA-event timed
   e2e        same metric through the public API estimate_flow_batch with HOST (pinned) uint8 frames in and host
              float64 flow out, H2D/D2H inside the timed region
-  roofline   the PCG solver kernel: algorithmic bytes (272 B per pixel-iteration) / CUDA-event
+  roofline   the PCG solver kernel: algorithmic bytes (228 B per pixel-iteration) / CUDA-event
              time of the solves inside the timed region, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the NumPy/SciPy oracle port (oracle/flow_oracle.py) of the same preset timed on a bounded sample
 --impl reference: the CPU arm -- the oracle port on all host cores (one process per core, one sample pair each).
@@ -36,7 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "optical-flow-python_b200"))
 
 METHOD = "classic+nl-fast"
 H, W = 480, 640
-PCG_BYTES_PER_PIXEL_ITER = 272        # DESIGN.md section 5 / solve.cu header
+PCG_BYTES_PER_PIXEL_ITER = 228        # DESIGN.md section 4 / solve.cu header: phase A 152 B + phase B 76 B
 SAMPLE_H, SAMPLE_W = 120, 160         # CPU-baseline sample: centre crop with 1/16 of the pixels
 
 

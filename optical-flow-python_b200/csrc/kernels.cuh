@@ -27,8 +27,8 @@ struct LinSys {                // matrix-free 2N x 2N system, B systems of H x W
 };
 
 struct PcgWork {               // scratch vectors + reduction buffers for the persistent PCG kernel
-  double2 *r, *p, *Ap;
-  double *Minv;                // 3 planes: m11, m12, m22 (block-Jacobi inverse) [3][B*H*W]
+  double2 *r, *p, *p2, *z, *Ap; // residual, search direction (ping-pong), preconditioned residual, A p
+  float *Minv;                 // 3 planes: m11, m12, m22 (block-Jacobi inverse, fp32) [3][B*H*W]
   double *partial;             // [3][B][grid]
   double *scal;                // per-system scalars [8][B]
   int *flags;                  // [0]=ndone, [1..B]=done[b], then iters[b]

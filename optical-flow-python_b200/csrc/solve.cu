@@ -3,12 +3,13 @@
 // independent systems.  Replaces scipy.sparse.linalg.spsolve / cg behind BaseOpticalFlow._solve_linear_system
 // (base.py:87-136): the sparse matrix is never built.
 //
-// Per iteration (3 phases separated by grid.sync(); fp64; bytes per pixel):
-//   A  Ap = A p, partial p.Ap                read p 16, D 16, a12 8, WH 16, WV 16; write Ap 16          = 88
-//   B  x += a p, r -= a Ap, z = M^-1 r,      read x 16, r 16, p 16, Ap 16, Minv 24; write x 16, r 16,
-//      partial r.z, r.r                      z 16 (into the dead Ap buffer)                               = 136
-//   C  p = z + b p                           read z 16, p 16; write p 16                                 = 48
-//                                                                                            total        272 B
+// Per iteration: 2 phases separated by grid.sync(); fp64 vectors; algorithmic bytes per pixel:
+//   A  p = z + beta p_old (recomputed on the fly at the 5 stencil points, so the textbook "p update" pass and its
+//      grid sync disappear), x += alpha_prev p_old (deferred: p_old is in registers anyway), Ap = A p, partial p.Ap
+//        read z 16, p_old 16, x 16, D 16, a12 8, WH 16, WV 16; write p 16, x 16, Ap 16                   = 152
+//   B  r -= alpha Ap, z = M^-1 r, partial r.z, r.r
+//        read r 16, Ap 16, Minv 12 (fp32 block-Jacobi inverse); write r 16, z 16                           = 76
+//                                                                                            total        228 B
 // Dot products: per-thread accumulation -> warp shuffle tree -> shared -> one double per (CTA, system),
 // then every CTA re-reduces the per-CTA partials of the systems it owns in a fixed order, so all CTAs get
 // bit-identical scalars and results are run-to-run deterministic (no floating-point atomics).
@@ -91,7 +92,16 @@ __device__ __forceinline__ double2 apply_stencil(const Stencil &s, const double2
   return make_double2(au, av);
 }
 
-__global__ void __launch_bounds__(PCG_THREADS, 2) pcg_kernel(PcgParams P) {
+// p_new = z + beta * p_old at pixel j (computed on the fly: phase C of the textbook algorithm is fused into the matvec)
+__device__ __forceinline__ double2 pnew_at(const double2 *z, const double2 *pold, long long j, double beta) {
+  double2 zz = z[j], pp = pold[j];
+  return make_double2(zz.x + beta * pp.x, zz.y + beta * pp.y);
+}
+
+#ifndef PCG_MINB
+#define PCG_MINB 3
+#endif
+__global__ void __launch_bounds__(PCG_THREADS, PCG_MINB) pcg_kernel(PcgParams P) {
   cg::grid_group grid = cg::this_grid();
   const LinSys &S = P.sys;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -107,21 +117,22 @@ __global__ void __launch_bounds__(PCG_THREADS, 2) pcg_kernel(PcgParams P) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 
   __shared__ double sm_red[2][PCG_THREADS / 32];
-  __shared__ double s_rz[MAXLOC], s_bb[MAXLOC], s_coef[MAXLOC], s_rr[MAXLOC];
+  __shared__ double s_rz[MAXLOC], s_bb[MAXLOC], s_alpha[MAXLOC], s_beta[MAXLOC], s_rr[MAXLOC];
   __shared__ int s_done[MAXLOC];
 
   double *part_pap = P.w.partial;                      // [B][G]
   double *part_rz = P.w.partial + (long long)B * G;
   double *part_rr = P.w.partial + 2LL * B * G;
   double *part_bb = P.w.partial + 3LL * B * G;
-  double *Minv = P.w.Minv;
-  double2 *r = P.w.r, *p = P.w.p, *Ap = P.w.Ap, *x = P.x;
+  float *Minv = P.w.Minv;                               // [3][B*H*W] block-Jacobi inverse, fp32 (a preconditioner need not be exact)
+  double2 *r = P.w.r, *Ap = P.w.Ap, *z = P.w.z, *x = P.x;
+  double2 *pold = P.w.p, *pnew = P.w.p2;                // ping-pong search directions
   int *ndone = P.w.flags;                               // [0]
   int *done_g = P.w.flags + 1;                          // [B]
   int *iters_g = P.w.flags + 1 + B;                     // [B]
   double *relres_g = P.w.scal;                          // [B]
 
-  // tile iteration helper: calls f(b, local, i_global, x, y) for every pixel of this CTA's tiles of system b
+  // tile iteration helper: runs the body for every pixel (i, px, py) of this CTA's tiles of system bsys
 #define FOR_TILES_OF(bsys, ...)                                                                  \
   {                                                                                              \
     long long ta = (long long)(bsys) * tps > t0 ? (long long)(bsys) * tps : t0;                  \
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 2) pcg_kernel(PcgParams P) {
     }                                                                                            \
   }
 
-  // ---------------- init: x = 0, r = b, Minv, z = Minv r, p = z; partial r.z and b.b ----------------
+  // ---------------- init: x = 0, r = b, Minv, z = Minv r, p_old = 0; partial r.z and b.b ----------------
   for (int b = b_first; b <= b_last; ++b) {
     double acc_rz = 0.0, acc_bb = 0.0;
     FOR_TILES_OF(b, {
@@ -153,13 +164,15 @@ __global__ void __launch_bounds__(PCG_THREADS, 2) pcg_kernel(PcgParams P) {
         m22 = fabs(dvv) > 1e-12 ? 1.0 / dvv : 0.0;
         m12 = 0.0;
       }
-      Minv[i] = m11; Minv[n_all + i] = m12; Minv[2 * n_all + i] = m22;
+      float f11 = (float)m11, f12 = (float)m12, f22 = (float)m22;
+      Minv[i] = f11; Minv[n_all + i] = f12; Minv[2 * n_all + i] = f22;
       double2 rb = __ldg(&S.rhs[i]);
-      double2 z = make_double2(m11 * rb.x + m12 * rb.y, m12 * rb.x + m22 * rb.y);
+      double2 zz = make_double2((double)f11 * rb.x + (double)f12 * rb.y, (double)f12 * rb.x + (double)f22 * rb.y);
       x[i] = make_double2(0.0, 0.0);
       r[i] = rb;
-      p[i] = z;
-      acc_rz += rb.x * z.x + rb.y * z.y;
+      z[i] = zz;
+      pold[i] = make_double2(0.0, 0.0);
+      acc_rz += rb.x * zz.x + rb.y * zz.y;
       acc_bb += rb.x * rb.x + rb.y * rb.y;
     })
     block_sum2(acc_rz, acc_bb, sm_red);
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 2) pcg_kernel(PcgParams P) {
       double bb = reduce_partials(part_bb, G, b, c_lo, c_hi);
       if (threadIdx.x == 0) {
         int l = b - b_first;
-        s_rz[l] = rz; s_bb[l] = bb; s_rr[l] = bb;
+        s_rz[l] = rz; s_bb[l] = bb; s_rr[l] = bb; s_alpha[l] = 0.0; s_beta[l] = 0.0;
         int dn = !(bb > 0.0) || !(rz > 0.0);          // zero right-hand side: x = 0 is the solution
         s_done[l] = dn;
         if (dn && cta == c_lo) { done_g[b] = 1; iters_g[b] = 0; relres_g[b] = 0.0; atomicAdd(ndone, 1); }
@@ -185,46 +198,77 @@ __global__ void __launch_bounds__(PCG_THREADS, 2) pcg_kernel(PcgParams P) {
 
   int k = 0;
   for (; k < P.maxit; ++k) {
-    if (*(volatile int *)ndone >= B) break;
-    // ---------------- phase A ----------------
+    // ---------------- phase A: p = z + beta p_old (on the fly, 5 points), x += alpha_prev p_old, Ap = A p ----------------
     for (int b = b_first; b <= b_last; ++b) {
-      if (s_done[b - b_first]) continue;
+      const int l = b - b_first;
+      if (s_done[l]) continue;
+      const double beta = s_beta[l], aprev = s_alpha[l];
       double acc = 0.0, dummy = 0.0;
       FOR_TILES_OF(b, {
-        Stencil s = load_stencil(S, i, px, py);
-        double2 a = apply_stencil(s, p, i, px, py, H, W);
-        double2 pc = p[i];
-        Ap[i] = a;
-        acc += pc.x * a.x + pc.y * a.y;
+        // branch-free gather: every load is issued unconditionally at a clamped (always valid) address so that all
+        // ~16 of them are in flight together; out-of-image neighbours are then replaced by the centre value
+        // (difference 0) -- their edge weights are 0 by construction anyway (no edge leaves the last column / row)
+        const long long jl = i > 0 ? i - 1 : 0, jr = i + 1 < n_all ? i + 1 : n_all - 1;
+        const long long ju = i >= W ? i - W : 0, jd = i + W < n_all ? i + W : n_all - 1;
+        const double2 zc = z[i], po = pold[i];
+        const double2 zl = z[jl], pl = pold[jl], zr = z[jr], pr = pold[jr];
+        const double2 zu = z[ju], pu = pold[ju], zd = z[jd], pd = pold[jd];
+        const double2 sd = __ldg(&S.D[i]), swr = __ldg(&S.WH[i]), swd = __ldg(&S.WV[i]);
+        const double2 swl = __ldg(&S.WH[jl]), swu = __ldg(&S.WV[ju]);
+        const double sa12 = __ldg(&S.a12[i]);
+        const double2 c = make_double2(zc.x + beta * po.x, zc.y + beta * po.y);
+        double2 nl = make_double2(zl.x + beta * pl.x, zl.y + beta * pl.y);
+        double2 nr = make_double2(zr.x + beta * pr.x, zr.y + beta * pr.y);
+        double2 nu = make_double2(zu.x + beta * pu.x, zu.y + beta * pu.y);
+        double2 nd = make_double2(zd.x + beta * pd.x, zd.y + beta * pd.y);
+        if (px == 0) nl = c;
+        if (px + 1 >= W) nr = c;
+        if (py == 0) nu = c;
+        if (py + 1 >= H) nd = c;
+        double au = sd.x * c.x + sa12 * c.y;
+        double av = sa12 * c.x + sd.y * c.y;
+        au += swr.x * (c.x - nr.x); av += swr.y * (c.y - nr.y);
+        au += swl.x * (c.x - nl.x); av += swl.y * (c.y - nl.y);
+        au += swd.x * (c.x - nd.x); av += swd.y * (c.y - nd.y);
+        au += swu.x * (c.x - nu.x); av += swu.y * (c.y - nu.y);
+        if (k > 0) {                                   // deferred x update of the previous iteration (p_old is in registers)
+          double2 xc = x[i];
+          x[i] = make_double2(xc.x + aprev * po.x, xc.y + aprev * po.y);
+        }
+        pnew[i] = c;
+        Ap[i] = make_double2(au, av);
+        acc += c.x * au + c.y * av;
       })
       block_sum2(acc, dummy, sm_red);
       if (threadIdx.x == 0) part_pap[(long long)b * G + cta] = acc;
     }
     grid.sync();
+    // Termination test placed HERE on purpose: ndone is only incremented between the second grid.sync of an
+    // iteration and the first grid.sync of the next one, so every CTA reads the same value at this point.
+    if (*(volatile int *)ndone >= B) break;
     if (threadIdx.x < 32) {
       for (int b = b_first; b <= b_last; ++b) {
         int l = b - b_first;
         if (s_done[l]) continue;
         int c_lo = (int)(((long long)b * tps) / tpc), c_hi = (int)((((long long)(b + 1)) * tps - 1) / tpc);
         double pap = reduce_partials(part_pap, G, b, c_lo, c_hi);
-        if (threadIdx.x == 0) s_coef[l] = pap > 0.0 ? s_rz[l] / pap : 0.0;   // alpha (0 => breakdown, handled below)
+        if (threadIdx.x == 0) s_alpha[l] = pap > 0.0 ? s_rz[l] / pap : 0.0;   // 0 => breakdown, handled below
       }
     }
     __syncthreads();
-    // ---------------- phase B ----------------
+    // ---------------- phase B: r -= alpha Ap, z = M^-1 r, partial r.z and r.r ----------------
     for (int b = b_first; b <= b_last; ++b) {
       int l = b - b_first;
       if (s_done[l]) continue;
-      double alpha = s_coef[l];
+      double alpha = s_alpha[l];
       double acc_rz = 0.0, acc_rr = 0.0;
       FOR_TILES_OF(b, {
-        double2 xc = x[i], rc = r[i], pc = p[i], ac = Ap[i];
-        xc.x += alpha * pc.x; xc.y += alpha * pc.y;
+        double2 rc = r[i], ac = Ap[i];
         rc.x -= alpha * ac.x; rc.y -= alpha * ac.y;
-        double m11 = Minv[i], m12 = Minv[n_all + i], m22 = Minv[2 * n_all + i];
-        double2 z = make_double2(m11 * rc.x + m12 * rc.y, m12 * rc.x + m22 * rc.y);
-        x[i] = xc; r[i] = rc; Ap[i] = z;
-        acc_rz += rc.x * z.x + rc.y * z.y;
+        double m11 = (double)Minv[i], m12 = (double)Minv[n_all + i], m22 = (double)Minv[2 * n_all + i];
+        double2 zz = make_double2(m11 * rc.x + m12 * rc.y, m12 * rc.x + m22 * rc.y);
+        r[i] = rc; z[i] = zz;
+        acc_rz += rc.x * zz.x + rc.y * zz.y;
         acc_rr += rc.x * rc.x + rc.y * rc.y;
       })
       block_sum2(acc_rz, acc_rr, sm_red);
@@ -239,14 +283,13 @@ __global__ void __launch_bounds__(PCG_THREADS, 2) pcg_kernel(PcgParams P) {
         double rz = reduce_partials(part_rz, G, b, c_lo, c_hi);
         double rr = reduce_partials(part_rr, G, b, c_lo, c_hi);
         if (threadIdx.x == 0) {
-          double alpha = s_coef[l];
-          double beta = s_rz[l] > 0.0 ? rz / s_rz[l] : 0.0;
+          double alpha = s_alpha[l];
+          s_beta[l] = s_rz[l] > 0.0 ? rz / s_rz[l] : 0.0;
           s_rz[l] = rz;
           s_rr[l] = rr;
-          s_coef[l] = beta;
           int dn = (rr <= P.tol2 * s_bb[l]) || !(alpha > 0.0) || !(rz > 0.0) || !(rr == rr);
           if (dn) {
-            s_done[l] = 1;
+            s_done[l] = 2;                              // 2: finished in this iteration, x still lacks alpha_k p_k
             if (cta == c_lo) {
               done_g[b] = (rr <= P.tol2 * s_bb[l]) ? 1 : 2;
               iters_g[b] = k + 1;
@@ -258,20 +301,34 @@ __global__ void __launch_bounds__(PCG_THREADS, 2) pcg_kernel(PcgParams P) {
       }
     }
     __syncthreads();
-    // ---------------- phase C ----------------
+    // final x update of systems that just finished (own pixels only: no grid sync needed)
     for (int b = b_first; b <= b_last; ++b) {
       int l = b - b_first;
-      if (s_done[l]) continue;
-      double beta = s_coef[l];
+      if (s_done[l] != 2) continue;
+      double alpha = s_alpha[l];
       FOR_TILES_OF(b, {
-        double2 z = Ap[i], pc = p[i];
-        p[i] = make_double2(z.x + beta * pc.x, z.y + beta * pc.y);
+        double2 xc = x[i], pc = pnew[i];
+        x[i] = make_double2(xc.x + alpha * pc.x, xc.y + alpha * pc.y);
       })
     }
-    grid.sync();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int b = b_first; b <= b_last; ++b)
+        if (s_done[b - b_first] == 2) s_done[b - b_first] = 1;
+    __syncthreads();
+    { double2 *t = pold; pold = pnew; pnew = t; }
+  }
+  // systems that ran out of iterations: apply the pending x update (p_k now lives in pold) and report
+  for (int b = b_first; b <= b_last; ++b) {
+    int l = b - b_first;
+    if (s_done[l] || k == 0) continue;
+    double alpha = s_alpha[l];
+    FOR_TILES_OF(b, {
+      double2 xc = x[i], pc = pold[i];
+      x[i] = make_double2(xc.x + alpha * pc.x, xc.y + alpha * pc.y);
+    })
   }
 #undef FOR_TILES_OF
-  // systems that ran out of iterations
   if (threadIdx.x == 0) {
     for (int b = b_first; b <= b_last; ++b) {
       int l = b - b_first;
@@ -303,7 +360,7 @@ __global__ void pcg_stats_kernel(const int *flags, int B, long long hw, long lon
 
 size_t pcg_work_bytes(const b200flow_ctx *ctx, int B, int H, int W) {
   size_t n = (size_t)B * H * W;
-  return n * (3 * sizeof(double2) + 3 * sizeof(double)) + 4 * (size_t)B * ctx->num_sms * 8 * 8 + 64 * B + 4096;
+  return n * (5 * sizeof(double2) + 3 * sizeof(float)) + 4 * (size_t)B * ctx->num_sms * 8 * 8 + 64 * B + 4096;
 }
 
 static int pcg_grid(b200flow_ctx *ctx, int *grid_out) {
@@ -326,6 +383,8 @@ int pcg_work_alloc(b200flow_ctx *ctx, int B, int H, int W, PcgWork *w) {
   w->grid = G;
   BF_TRY(arena_alloc(ctx, &w->r, n));
   BF_TRY(arena_alloc(ctx, &w->p, n));
+  BF_TRY(arena_alloc(ctx, &w->p2, n));
+  BF_TRY(arena_alloc(ctx, &w->z, n));
   BF_TRY(arena_alloc(ctx, &w->Ap, n));
   BF_TRY(arena_alloc(ctx, &w->Minv, 3 * n));
   BF_TRY(arena_alloc(ctx, &w->partial, (size_t)4 * B * G));
