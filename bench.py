@@ -16,7 +16,7 @@ One JSON line on rank 0:
   value      frame-pairs/s, whole job, inputs already resident in HBM (b200flow_estimate_rgb8_dev), CUDA-event timed
   e2e        same metric through the public API estimate_flow_batch with HOST (pinned) uint8 frames in and host
              float64 flow out, H2D/D2H inside the timed region
-  roofline   the PCG solver kernel: algorithmic bytes (228 B per pixel-iteration) / CUDA-event
+  roofline   the PCG solver kernel: algorithmic bytes (120 B per pixel-iteration mixed / 228 B fp64) / CUDA-event
              time of the solves inside the timed region, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the NumPy/SciPy oracle port (oracle/flow_oracle.py) of the same preset timed on a bounded sample
 --impl reference: the CPU arm -- the oracle port on all host cores (one process per core, one sample pair each).
@@ -36,7 +36,10 @@ sys.path.insert(0, os.path.join(ROOT, "optical-flow-python_b200"))
 
 METHOD = "classic+nl-fast"
 H, W = 480, 640
-PCG_BYTES_PER_PIXEL_ITER = 228        # DESIGN.md section 4 / solve.cu header: phase A 152 B + phase B 76 B
+# algorithmic bytes per pixel per PCG iteration (DESIGN.md section 4 / solve.cu headers):
+#   mixed (default): fp32 Krylov vectors + fp32 coefficient copy, phase A 76 B + phase B 44 B
+#   fp64           : every vector fp64, phase A 152 B + phase B 76 B
+PCG_BYTES = {"mixed": 120, "fp64": 228}
 SAMPLE_H, SAMPLE_W = 120, 160         # CPU-baseline sample: centre crop with 1/16 of the pixels
 
 
@@ -200,6 +203,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="frame pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver-precision", default="mixed", choices=["mixed", "fp64"],
+                    help="mixed: fp32 Krylov vectors with fp64 reliable updates (default); fp64: all-fp64 PCG (variant)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -225,7 +230,9 @@ def main():
 
     ims1, ims2, flow_gt = make_batch(B, 3 + rank * B)            # every rank its own pairs (weak scaling)
     ctx = _lib.default_context(local_rank)
+    PCG_BYTES_PER_PIXEL_ITER = PCG_BYTES[args.solver_precision]
     ope = load_of_method(METHOD)
+    ope.solver_precision = args.solver_precision
     ope.pyramid_levels = ope._auto_pyramid_levels(np.empty((H, W, 2)))
     P = ope._c_params(levels=ope.pyramid_levels)
     ope._apply_solver(P)
@@ -277,11 +284,11 @@ def main():
     h1 = torch.from_numpy(ims1).pin_memory().numpy()
     h2 = torch.from_numpy(ims2).pin_memory().numpy()
     for _ in range(2):
-        uv_host = estimate_flow_batch(h1, h2, METHOD, device=local_rank)
+        uv_host = estimate_flow_batch(h1, h2, METHOD, params={"solver_precision": args.solver_precision}, device=local_rank)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        uv_host = estimate_flow_batch(h1, h2, METHOD, device=local_rank)
+        uv_host = estimate_flow_batch(h1, h2, METHOD, params={"solver_precision": args.solver_precision}, device=local_rank)
     barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
@@ -326,12 +333,16 @@ def main():
                                    "%d pairs per GPU per step" % B,
                        "method": METHOD, "height": H, "width": W, "pairs_per_gpu_per_step": B,
                        "parallelism": "independent frame pairs per GPU, no collective",
-                       "solver": "block-Jacobi PCG to relative residual %g (stands in for spsolve)" % P.tol,
+                       "solver": "block-Jacobi PCG until the fp64 true residual ||b-Ax|| <= %g ||b|| (stands in for spsolve); %s"
+                                 % (P.tol, "Krylov vectors fp32, solution + residual replacement fp64" if
+                                    args.solver_precision == "mixed" else "all vectors fp64"),
+                       "solver_precision": args.solver_precision,
                        "l2": "per-step working set ~%.1f GB per GPU >> 126 MB L2; no flush needed" % (B * H * W * 450 / 1e9)},
             "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(2 * B * H * W * 3), "d2h_bytes_per_step": int(B * H * W * 2 * 8)},
             "gpu_launches": int(launches_all),
-            "roofline": {"kernel": "pcg_kernel (persistent cooperative PCG, solve.cu)", "bound": "hbm",
+            "roofline": {"kernel": "%s (persistent cooperative PCG, solve.cu)" %
+                                   ("pcg_mixed_kernel" if args.solver_precision == "mixed" else "pcg_kernel"), "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "bytes_per_pixel_iter": PCG_BYTES_PER_PIXEL_ITER, "pixel_iters_per_step": pixel_iters / args.steps,

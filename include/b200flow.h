@@ -41,8 +41,11 @@ typedef struct { int kind; double p0, p1; } b200flow_penalty;
 
 enum { B200FLOW_HS = 0, B200FLOW_BA = 1, B200FLOW_CLASSICNL = 2 };
 enum { B200FLOW_INTERP_BICUBIC = 0, B200FLOW_INTERP_CUBIC = 1, B200FLOW_INTERP_BILINEAR = 2 };
-enum { B200FLOW_SOLVER_EXACT = 0,   /* replaces 'backslash' (spsolve): block-Jacobi PCG run to `tol` */
-       B200FLOW_SOLVER_PCG = 1 };   /* the reference's own approximate 'pcg' mode (Jacobi, rtol/maxiter as given) */
+enum { B200FLOW_SOLVER_EXACT = 0,   /* replaces 'backslash' (spsolve): block-Jacobi PCG run until the fp64 TRUE residual
+                                       ||b - A x|| <= tol ||b||; Krylov vectors in fp32, solution and residual
+                                       replacement ("reliable updates") in fp64 */
+       B200FLOW_SOLVER_PCG = 1,     /* the reference's own approximate 'pcg' mode (Jacobi, rtol/maxiter as given), all fp64 */
+       B200FLOW_SOLVER_EXACT_F64 = 2 }; /* as EXACT with every vector in fp64 (the round-1 kernel; reported variant) */
 
 /* Mirrors the public attributes of HSOpticalFlow / BAOpticalFlow / ClassicNLOpticalFlow
  * (methods/base.py:21-63, hs.py:23-47, ba.py:26-55, classic_nl.py:32-87; presets methods/config.py:10-176). */
@@ -150,6 +153,12 @@ int b200flow_detect_occlusion(b200flow_ctx*, const double *uv, const double *ima
 /* utils/weighted_median.py:24-112: uv (H,W,2), color (H,W,C) C in {1,3}, occ (H,W) -> out (H,W,2) */
 int b200flow_weighted_median(b200flow_ctx*, const double *uv, const double *color, const double *occ,
                              int H, int W, int C, int hsz, double sigma_i, double *out);
+
+
+/* ---- diagnostics (bench.py / ncu; no reference counterpart): CUDA-event time of `reps` solves of a synthetic batch of B
+ *      random SPD five-point systems (coefficients spanning `decades` decades) run for exactly `iters` iterations */
+int b200flow_debug_pcg_bench(b200flow_ctx*, int B, int H, int W, int solver, int iters, int reps, double decades,
+                             double *ms_per_solve, long long *iters_done);
 
 #ifdef __cplusplus
 }

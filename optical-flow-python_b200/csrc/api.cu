@@ -376,18 +376,73 @@ int b200flow_solve_increment(b200flow_ctx *ctx, const b200flow_params *p, double
   LinSys sys;
   BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, &sys));
   if (!(p->tol > 0.0) || p->maxit < 1) return set_err(ctx, B200FLOW_EINVAL, "solver tol/maxit invalid");
-  if (p->solver != B200FLOW_SOLVER_EXACT && p->solver != B200FLOW_SOLVER_PCG)
+  if (p->solver != B200FLOW_SOLVER_EXACT && p->solver != B200FLOW_SOLVER_PCG && p->solver != B200FLOW_SOLVER_EXACT_F64)
     return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
   size_t N = (size_t)H * W;
   PcgWork w;
   double2 *d_x;
   BF_TRY(pcg_work_alloc(ctx, 1, H, W, &w));
   BF_TRY(arena_alloc(ctx, &d_x, N));
-  int rc = k_pcg_solve(ctx, sys, w, d_x, p->tol, p->maxit, p->solver == B200FLOW_SOLVER_PCG, iters, relres, true);
+  int rc = k_pcg_solve(ctx, sys, w, d_x, p->tol, p->maxit, pcg_mode_of(p->solver), iters, relres, true);
   if (rc < 0 && rc != B200FLOW_ENOCONV) return rc;
   BF_TRY(download(ctx, x, (const double *)d_x, 2 * N));
   API_SYNC(ctx);
   return rc;
+}
+
+// Diagnostic (bench / ncu only, not on the flow path): time `reps` solves of a synthetic batch of B five-point systems
+// of H x W pixels (random SPD coefficients spanning `decades` decades) run for exactly `iters` iterations each.
+__global__ void synth_system_kernel(bf::LinSys S, double decades, unsigned seed) {
+  long long n = (long long)S.B * S.H * S.W;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x = (int)(i % S.W), y = (int)((i / S.W) % S.H);
+  auto rnd = [&](unsigned k) {
+    unsigned long long z = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed + k * 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  };
+  double ix = 20.0 * (rnd(0) - 0.5), iy = 20.0 * (rnd(1) - 0.5), d = 1e-7 * pow(10.0, decades * rnd(2));   // weak data term: Poisson-like, hundreds of iterations
+  S.D[i] = make_double2(d * ix * ix, d * iy * iy);
+  S.a12[i] = d * ix * iy;
+  double wh = x + 1 < S.W ? pow(10.0, decades * rnd(3)) : 0.0, wv = y + 1 < S.H ? pow(10.0, decades * rnd(4)) : 0.0;
+  S.WH[i] = make_double2(wh, x + 1 < S.W ? pow(10.0, decades * rnd(5)) : 0.0);
+  S.WV[i] = make_double2(wv, y + 1 < S.H ? pow(10.0, decades * rnd(6)) : 0.0);
+  S.rhs[i] = make_double2(rnd(7) - 0.5, rnd(8) - 0.5);
+}
+
+int b200flow_debug_pcg_bench(b200flow_ctx *ctx, int B, int H, int W, int solver, int iters, int reps, double decades,
+                             double *ms_per_solve, long long *iters_done) {
+  API_BEGIN(ctx);
+  if (B < 1 || H < 1 || W < 1 || iters < 1 || reps < 1) return set_err(ctx, B200FLOW_EINVAL, "bad arguments");
+  LinSys sys;
+  PcgWork w;
+  double2 *x;
+  long long *dstats;
+  BF_TRY(alloc_linsys(ctx, B, H, W, &sys));
+  BF_TRY(pcg_work_alloc(ctx, B, H, W, &w));
+  BF_TRY(arena_alloc(ctx, &x, (size_t)B * H * W));
+  BF_TRY(arena_alloc(ctx, &dstats, 4));
+  long long n = (long long)B * H * W;
+  BF_LAUNCH(ctx, synth_system_kernel, (unsigned)cdiv(n, 256), 256, 0, sys, decades, 12345u);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  BF_TRY(k_pcg_solve_async(ctx, sys, w, x, 1e-30, iters, pcg_mode_of(solver), nullptr));   // warm-up
+  BF_CUDA(ctx, cudaMemsetAsync(dstats, 0, 4 * sizeof(long long), ctx->stream));
+  cudaEventRecord(e0, ctx->stream);
+  for (int r = 0; r < reps; ++r) BF_TRY(k_pcg_solve_async(ctx, sys, w, x, 1e-30, iters, pcg_mode_of(solver), dstats));
+  cudaEventRecord(e1, ctx->stream);
+  long long hs[4];
+  BF_CUDA(ctx, cudaMemcpyAsync(hs, dstats, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
+  BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_per_solve) *ms_per_solve = ms / reps;
+  if (iters_done) *iters_done = hs[0] / reps;
+  return 0;
 }
 
 int b200flow_median_filter(b200flow_ctx *ctx, const double *uv, int H, int W, int kh, int kw, double *out) {

@@ -32,7 +32,7 @@ struct PcgWork {               // scratch vectors + reduction buffers for the pe
   double *partial;             // [3][B][grid]
   double *scal;                // per-system scalars [8][B]
   int *flags;                  // [0]=ndone, [1..B]=done[b], then iters[b]
-  int grid;
+  int grid, grid_mixed;        // resident grid sizes of pcg_kernel / pcg_mixed_kernel
 };
 
 // ---- pre.cu
@@ -68,9 +68,14 @@ int k_robust_eval(b200flow_ctx *, b200flow_penalty pen, int d_type, const double
 // ---- solve.cu
 size_t pcg_work_bytes(const b200flow_ctx *, int B, int H, int W);
 int pcg_work_alloc(b200flow_ctx *, int B, int H, int W, PcgWork *w);
-int k_pcg_solve(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int scalar_jacobi,
+// mode: how `solver` of b200flow_params maps onto the two persistent kernels
+enum { PCG_MODE_MIXED = 0,        // block-Jacobi PCG, fp32 Krylov vectors + fp64 reliable updates (B200FLOW_SOLVER_EXACT)
+       PCG_MODE_JACOBI_F64 = 1,   // scalar-Jacobi all-fp64 PCG: the reference's own 'pcg' mode (B200FLOW_SOLVER_PCG)
+       PCG_MODE_BLOCK_F64 = 2 };  // block-Jacobi all-fp64 PCG (B200FLOW_SOLVER_EXACT_F64)
+inline int pcg_mode_of(int solver) { return solver; }
+int k_pcg_solve(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                 int *iters_host /*[B] or null*/, double *relres_host /*[B] or null*/, bool sync_results);
-int k_pcg_solve_async(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int scalar_jacobi,
+int k_pcg_solve_async(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                       long long *stats_dev);
 int k_operator_apply(b200flow_ctx *, LinSys sys, const double2 *x, double2 *Ax, double2 *diag);
 

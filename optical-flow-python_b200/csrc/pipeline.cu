@@ -78,7 +78,7 @@ int check_params(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
   if (B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad batch/size B=%d H=%d W=%d", B, H, W);
   if (p->method < 0 || p->method > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown method %d", p->method);
   if (p->interp < 0 || p->interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", p->interp);
-  if (p->solver != B200FLOW_SOLVER_EXACT && p->solver != B200FLOW_SOLVER_PCG)
+  if (p->solver != B200FLOW_SOLVER_EXACT && p->solver != B200FLOW_SOLVER_PCG && p->solver != B200FLOW_SOLVER_EXACT_F64)
     return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
   if (!(p->pyramid_spacing > 1.0) || p->pyramid_spacing > 8.0)
     return set_err(ctx, B200FLOW_EINVAL, "pyramid_spacing %g out of range (1, 8]", p->pyramid_spacing);
@@ -127,6 +127,7 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
   const size_t N = (size_t)B * HW;
   const bool hs = p->method == B200FLOW_HS, cnl = p->method == B200FLOW_CLASSICNL;
   const int launches0 = ctx->launches;
+  const bool trace = getenv("B200FLOW_TRACE") != nullptr;
   StageTimer tm(ctx);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->timing) {
@@ -198,7 +199,7 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
 
   const int mh = p->median_h, mw = p->median_w;
   const bool have_median = mh > 0 && mw > 0;
-  const int scalar_jacobi = p->solver == B200FLOW_SOLVER_PCG;
+  const int pcg_mode = pcg_mode_of(p->solver);
   int solves = 0;
 
   const int gnc_stages = hs ? 1 : p->gnc_iters;
@@ -236,8 +237,20 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
             BF_TRY(k_assemble_from_deriv(ctx, It, Ix, Iy, cur, dcur, B, h, w, ps, sys));
           tm.end();
           tm.begin(T_SOLVE);
-          BF_TRY(k_pcg_solve_async(ctx, sys, work, x, p->tol, p->maxit, scalar_jacobi, dstats));
+          BF_TRY(k_pcg_solve_async(ctx, sys, work, x, p->tol, p->maxit, pcg_mode, dstats));
           tm.end();
+          if (trace) {   // B200FLOW_TRACE=1 (debug): per-solve time and per-system iteration counts; synchronises
+            std::vector<int> fl(1 + 2 * B);
+            cudaMemcpyAsync(fl.data(), work.flags, sizeof(int) * fl.size(), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            float ms = 0.f;
+            if (tm.on) cudaEventElapsedTime(&ms, tm.spans.back().a, tm.spans.back().b);
+            int mn = 1 << 30, mx = 0; long long sum = 0;
+            for (int b = 0; b < B; ++b) { int v = fl[1 + B + b]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; }
+            fprintf(stderr, "[b200flow trace] gnc %d level %d (%dx%d) warp %d: solve %.3f ms, iters min %d mean %.1f max %d, "
+                            "%.1f us/iter(max), alg %.0f GB/s\n", ignc, l, h, w, it, ms, mn, (double)sum / B, mx,
+                    mx ? 1e3 * ms / mx : 0.0, ms > 0 ? (double)sum * hw * (pcg_mode == PCG_MODE_MIXED ? 120 : 228) / (ms * 1e6) : 0.0);
+          }
           solves++;
           tm.begin(T_FILTER);
           if (hs) {

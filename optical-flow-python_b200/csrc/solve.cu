@@ -23,6 +23,7 @@ namespace bf {
 constexpr int PCG_THREADS = 256;
 constexpr int TILE_W = 32, TILE_H = 8;
 constexpr int MAXLOC = 32;       // systems one CTA may touch
+constexpr double PCG_RELIABLE_DELTA = 0.01;  // mixed precision: fp64 residual replacement when |r| fell 100x
 
 struct PcgParams {
   LinSys sys;
@@ -342,6 +343,448 @@ __global__ void __launch_bounds__(PCG_THREADS, PCG_MINB) pcg_kernel(PcgParams P)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mixed-precision PCG with reliable updates (the default "exact" solver).
+//
+// The Krylov vectors r, z, p, Ap and the partial solution y live in fp32, as does a copy of the stencil
+// coefficients; the solution x is accumulated in fp64 and, whenever the iterated fp32 residual has dropped by
+// `delta` since the last update (or claims convergence), the TRUE residual r = b - A x is recomputed in fp64 from
+// the fp64 coefficients and replaces the iterated one ("reliable update": the search direction is kept, so CG does
+// not restart).  Convergence is only ever declared on that fp64 true residual, so the result satisfies the same
+// ||b - A x|| <= tol ||b|| criterion as the all-fp64 kernel above; on the Classic+NL systems the iteration counts
+// are identical (scripts/mp_proto.py: 470 vs 470 iterations on RubberWhale full resolution, alpha = 0).
+//
+// Algorithmic bytes per pixel-iteration (fp32 working set):
+//   A  read z 8, p_old 8, y 8, D 8, a12 4, WH 8, WV 8; write p 8, y 8, Ap 8                              = 76
+//   B  read r 8, Ap 8, Minv 12; write r 8, z 8                                                            = 44
+//                                                                                            total        120 B
+// plus, per reliable update (every 20-100 iterations), ONE extra phase and grid barrier: r = b - A (x + y + alpha p)
+// evaluated on the fly at the five stencil points (x 16, y 8, p 8, fp64 coefficients 72, b 16, Minv 12; write r, z 16
+// = 148 B); the flush x += y + alpha p itself rides on the next phase A.
+//
+// Every CTA keeps the scalars of ALL systems of the batch (reduced redundantly from the per-CTA partials in a fixed
+// order), so every control decision -- reliable update now? system finished? loop done? -- is taken identically by
+// every CTA without flags, atomics or extra grid barriers.  The same shared knowledge lets the tiles of the systems that
+// are still ACTIVE be re-dealt over the whole grid each time a system finishes, so a batch whose systems need different
+// iteration counts keeps every SM streaming until the last one is done.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXB = 128;        // systems per mixed-precision solve (one scalar-update thread per system)
+
+struct MixWork {
+  float2 *r, *z, *p, *p2, *Ap, *y;
+  float2 *D, *WH, *WV;
+  float *a12;
+};
+
+struct MixParams {
+  LinSys sys;
+  PcgWork w;
+  MixWork m;
+  double2 *x;
+  double tol2, delta2;
+  int maxit;
+  int tiles_x, tiles_y, tiles_per_sys;
+};
+
+// cold paths of the mixed kernel (initialisation, reliable update)
+__device__ __forceinline__ double2 mix_init_pixel(const MixParams &P, long long i, int px, int py, long long n_all,
+                                               float2 *pold) {
+  const LinSys &S = P.sys;
+  Stencil s = load_stencil(S, i, px, py);
+  double duu = s.d.x + s.wr.x + s.wl.x + s.wd.x + s.wu.x;
+  double dvv = s.d.y + s.wr.y + s.wl.y + s.wd.y + s.wu.y;
+  double m11, m12, m22;
+  double det = duu * dvv - s.a12 * s.a12;
+  if (det > 0.0 && det > 1e-14 * fabs(duu * dvv)) {
+    double inv = 1.0 / det;
+    m11 = dvv * inv; m22 = duu * inv; m12 = -s.a12 * inv;
+  } else {
+    m11 = fabs(duu) > 1e-12 ? 1.0 / duu : 0.0;
+    m22 = fabs(dvv) > 1e-12 ? 1.0 / dvv : 0.0;
+    m12 = 0.0;
+  }
+  float f11 = (float)m11, f12 = (float)m12, f22 = (float)m22;
+  float *Minv = P.w.Minv;
+  Minv[i] = f11; Minv[n_all + i] = f12; Minv[2 * n_all + i] = f22;
+  P.m.D[i] = make_float2((float)s.d.x, (float)s.d.y);
+  P.m.a12[i] = (float)s.a12;
+  P.m.WH[i] = make_float2((float)s.wr.x, (float)s.wr.y);
+  P.m.WV[i] = make_float2((float)s.wd.x, (float)s.wd.y);
+  double2 rb = __ldg(&S.rhs[i]);
+  float2 rs = make_float2((float)rb.x, (float)rb.y);
+  float2 zz = make_float2(f11 * rs.x + f12 * rs.y, f12 * rs.x + f22 * rs.y);
+  P.x[i] = make_double2(0.0, 0.0);
+  P.m.r[i] = rs; P.m.z[i] = zz;
+  pold[i] = make_float2(0.f, 0.f);
+  P.m.y[i] = make_float2(0.f, 0.f);
+  return make_double2((double)rs.x * (double)zz.x + (double)rs.y * (double)zz.y, rb.x * rb.x + rb.y * rb.y);
+}
+
+// true residual at pixel i of the solution x + y + alpha p (evaluated on the fly at the five stencil points)
+__device__ __forceinline__ double2 mix_reliable_pixel(const MixParams &P, long long i, int px, int py, long long n_all,
+                                                   const float2 *pnew, double alpha) {
+  const LinSys &S = P.sys;
+  const int W = S.W, H = S.H;
+  const double2 *x = P.x;
+  const float2 *y = P.m.y;
+  const long long jl = px > 0 ? i - 1 : i, jr = px + 1 < W ? i + 1 : i;
+  const long long ju = py > 0 ? i - W : i, jd = py + 1 < H ? i + W : i;
+#define XTRUE(j, out)                                                           \
+  {                                                                             \
+    double2 xx = x[j]; float2 yy = y[j], pp = pnew[j];                          \
+    out = make_double2(xx.x + ((double)yy.x + alpha * (double)pp.x),            \
+                       xx.y + ((double)yy.y + alpha * (double)pp.y));           \
+  }
+  double2 c, nl, nr, nu, nd;
+  XTRUE(i, c) XTRUE(jl, nl) XTRUE(jr, nr) XTRUE(ju, nu) XTRUE(jd, nd)
+#undef XTRUE
+  const double2 sd = __ldg(&S.D[i]), swr = __ldg(&S.WH[i]), swd = __ldg(&S.WV[i]);
+  const double2 swl = __ldg(&S.WH[jl]), swu = __ldg(&S.WV[ju]);   // multiplied by a zero difference when jl == i / ju == i
+  const double sa12 = __ldg(&S.a12[i]);
+  double au = sd.x * c.x + sa12 * c.y;
+  double av = sa12 * c.x + sd.y * c.y;
+  au += swr.x * (c.x - nr.x); av += swr.y * (c.y - nr.y);
+  au += swl.x * (c.x - nl.x); av += swl.y * (c.y - nl.y);
+  au += swd.x * (c.x - nd.x); av += swd.y * (c.y - nd.y);
+  au += swu.x * (c.x - nu.x); av += swu.y * (c.y - nu.y);
+  double2 rb = __ldg(&S.rhs[i]);
+  double ru = rb.x - au, rv = rb.y - av;
+  float2 rs = make_float2((float)ru, (float)rv);
+  const float *Minv = P.w.Minv;
+  float m11 = Minv[i], m12 = Minv[n_all + i], m22 = Minv[2 * n_all + i];
+  float2 zz = make_float2(m11 * rs.x + m12 * rs.y, m12 * rs.x + m22 * rs.y);
+  P.m.r[i] = rs; P.m.z[i] = zz;
+  return make_double2((double)rs.x * (double)zz.x + (double)rs.y * (double)zz.y, ru * ru + rv * rv);
+}
+
+// tuning (B200, round 1, bench workload): 2 CTAs/SM x 128 registers with phase A unrolled 2x beats 3 CTAs x 80 registers
+// (which spills): 256.7 vs 295.8 ms of solver time per 16-pair step
+#ifndef MIX_MINB
+#define MIX_MINB 2
+#endif
+#ifndef MIX_UA
+#define MIX_UA 2
+#endif
+#ifndef MIX_UB
+#define MIX_UB 4
+#endif
+
+__global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixParams P) {
+  cg::grid_group grid = cg::this_grid();
+  const LinSys &S = P.sys;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int H = S.H, W = S.W, B = S.B;
+  const long long HW = (long long)H * W;
+  const long long n_all = (long long)B * HW;
+  const int tps = P.tiles_per_sys;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  int GW = 32;
+  while (GW > 1 && B * GW > PCG_THREADS) GW >>= 1;
+
+  __shared__ double sm_red[2][PCG_THREADS / 32];
+  __shared__ double s_rz[MAXB], s_bb[MAXB], s_alpha[MAXB], s_beta[MAXB], s_maxr2[MAXB], s_rzprev[MAXB];
+  __shared__ double s_ta[MAXB], s_tb[MAXB];
+  __shared__ int s_state[MAXB];          // 0 active, 1 finished, 2 converged: final flush pending, 3 reliable update in progress
+  __shared__ int s_bad[MAXB], s_flush[MAXB];
+  __shared__ int s_act[MAXB], s_pos[MAXB];   // compact list of unfinished systems and its inverse
+  __shared__ int s_nact, s_tpc;
+
+  double *part_a = P.w.partial;                         // [B][G]  p.Ap
+  double *part_b = P.w.partial + (long long)B * G;      // [B][G]  r.z
+  double *part_c = P.w.partial + 2LL * B * G;           // [B][G]  r.r
+  float *Minv = P.w.Minv;
+  float2 *r = P.m.r, *z = P.m.z, *Ap = P.m.Ap, *y = P.m.y;
+  float2 *pold = P.m.p, *pnew = P.m.p2;
+  float2 *Df = P.m.D, *WHf = P.m.WH, *WVf = P.m.WV;
+  float *a12f = P.m.a12;
+  double2 *x = P.x;
+  int *done_g = P.w.flags + 1;
+  int *iters_g = P.w.flags + 1 + B;
+  double *relres_g = P.w.scal;
+
+  // ---- tile ownership: the tiles of the unfinished systems, in compact order, are dealt to the CTAs in contiguous
+  //      chunks of s_tpc tiles; recomputed (identically by every CTA) whenever a system finishes
+#define REMAP()                                                                         \
+  {                                                                                     \
+    __syncthreads();                                                                    \
+    if (tid == 0) {                                                                     \
+      int n = 0;                                                                        \
+      for (int b = 0; b < B; ++b) {                                                     \
+        if (s_state[b] != 1) { s_act[n] = b; s_pos[b] = n; ++n; } else s_pos[b] = -1;   \
+      }                                                                                 \
+      s_nact = n;                                                                       \
+      long long tt = (long long)n * tps;                                                \
+      s_tpc = tt > 0 ? (int)((tt + G - 1) / G) : 1;                                     \
+    }                                                                                   \
+    __syncthreads();                                                                    \
+  }
+  // first / last CTA that owns tiles of system b (b must be unfinished)
+#define C_LO(b) ((int)(((long long)s_pos[b] * tps) / s_tpc))
+#define C_HI(b) ((int)((((long long)(s_pos[b] + 1)) * tps - 1) / s_tpc))
+  // this CTA's range of compact system slots
+#define OWN_RANGE()                                                                              \
+  const long long t0 = (long long)cta * s_tpc;                                                   \
+  const long long tt_ = (long long)s_nact * tps;                                                 \
+  const long long t1 = t0 + s_tpc < tt_ ? t0 + s_tpc : tt_;                                      \
+  const int a_first = t0 < t1 ? (int)(t0 / tps) : 0;                                             \
+  const int a_last = t0 < t1 ? (int)((t1 - 1) / tps) : -1;
+#define TILE_RANGE(aslot)                                                                        \
+  const int b = s_act[aslot];                                                                    \
+  const long long tbase = (long long)(aslot) * tps;                                              \
+  const long long ta = tbase > t0 ? tbase : t0;                                                  \
+  const long long tb = tbase + tps < t1 ? tbase + tps : t1;                                      \
+  const long long base = (long long)b * HW;
+#define PIXEL_OF(t, px, py, i, ok)                                                               \
+  {                                                                                              \
+    int tl = (int)((t) - tbase);                                                                 \
+    px = (tl % P.tiles_x) * TILE_W + tx;                                                         \
+    py = (tl / P.tiles_x) * TILE_H + ty;                                                         \
+    ok = (t) < tb && px < W && py < H;                                                           \
+    i = ok ? base + (long long)py * W + px : base;                                               \
+  }
+  // every CTA reduces the partials of every system in `want` state, all systems at once: a group of GW threads
+  // (GW = 2..32, the largest power of two with B*GW <= 256) per system, fixed summation order
+#define REDUCE_ALL(pa, pb, want)                                                        \
+  {                                                                                     \
+    const int b = tid / GW, gl = tid % GW;                                              \
+    double va = 0.0, vb = 0.0;                                                          \
+    if (b < B && s_state[b] == (want)) {                                                \
+      const int c_lo = C_LO(b), c_hi = C_HI(b);                                         \
+      const volatile double *qa = (pa) + (long long)b * G;                              \
+      const volatile double *qb = (pb) ? (pb) + (long long)b * G : qa;                  \
+      for (int c = c_lo + gl; c <= c_hi; c += GW) { va += qa[c]; vb += qb[c]; }         \
+    }                                                                                   \
+    for (int o = GW >> 1; o > 0; o >>= 1) {                                             \
+      va += __shfl_xor_sync(0xffffffffu, va, o);                                        \
+      vb += __shfl_xor_sync(0xffffffffu, vb, o);                                        \
+    }                                                                                   \
+    if (b < B && gl == 0) { s_ta[b] = va; s_tb[b] = vb; }                               \
+    __syncthreads();                                                                    \
+  }
+
+  // ---------------- init ----------------
+  for (int b = tid; b < MAXB; b += PCG_THREADS) { s_state[b] = b < B ? 0 : 1; s_bad[b] = 0; s_flush[b] = 0; }
+  REMAP()
+  {
+    OWN_RANGE()
+    for (int a = a_first; a <= a_last; ++a) {
+      TILE_RANGE(a)
+      double acc_rz = 0.0, acc_bb = 0.0;
+      for (long long t = ta; t < tb; ++t) {
+        int px, py; long long i; bool ok;
+        PIXEL_OF(t, px, py, i, ok)
+        if (!ok) continue;
+        double2 d = mix_init_pixel(P, i, px, py, n_all, pold);
+        acc_rz += d.x; acc_bb += d.y;
+      }
+      block_sum2(acc_rz, acc_bb, sm_red);
+      if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_bb; }
+    }
+  }
+  grid.sync();
+  REDUCE_ALL(part_b, part_c, 0)
+  if (tid < B) {
+    const int b = tid;
+    double rz = s_ta[b], bb = s_tb[b];
+    s_rz[b] = rz; s_bb[b] = bb; s_maxr2[b] = bb; s_alpha[b] = 0.0; s_beta[b] = 0.0; s_rzprev[b] = rz;
+    if (!(bb > 0.0) || !(rz > 0.0)) {                    // zero right-hand side: x = 0 is the solution
+      if (cta == C_LO(b)) { done_g[b] = 1; iters_g[b] = 0; relres_g[b] = 0.0; }
+      s_state[b] = 1;
+    }
+  }
+  REMAP()
+  int n_active = s_nact;
+
+  int k = 0;
+  for (; k < P.maxit && n_active > 0; ++k) {
+    OWN_RANGE()
+    // ---------------- phase A: p = z + beta p_old (on the fly), y += alpha_prev p_old, Ap = A p ----------------
+    for (int a = a_first; a <= a_last; ++a) {
+      TILE_RANGE(a)
+      const float beta = (float)s_beta[b], aprev = (float)s_alpha[b];
+      const double aprev_d = s_alpha[b];
+      const bool flush = s_flush[b] != 0;       // a reliable update happened: fold y + alpha p into the fp64 solution now
+      double acc = 0.0, dummy = 0.0;
+      for (long long t = ta; t < tb; t += MIX_UA) {
+        int px[MIX_UA], py[MIX_UA]; long long i[MIX_UA]; bool ok[MIX_UA];
+        float2 zc[MIX_UA], po[MIX_UA], zl[MIX_UA], pl[MIX_UA], zr[MIX_UA], pr[MIX_UA], zu[MIX_UA], pu[MIX_UA], zd[MIX_UA],
+            pd[MIX_UA], sd[MIX_UA], swr[MIX_UA], swd[MIX_UA], swl[MIX_UA], swu[MIX_UA], yc[MIX_UA];
+        float sa12[MIX_UA];
+#pragma unroll
+        for (int u = 0; u < MIX_UA; ++u) {
+          PIXEL_OF(t + u, px[u], py[u], i[u], ok[u])
+          // branch-free gather at clamped (always valid) addresses; out-of-image neighbours are replaced by the
+          // centre value below (their edge weights are 0 by construction anyway)
+          const long long ii = i[u];
+          const long long jl = ii > 0 ? ii - 1 : 0, jr = ii + 1 < n_all ? ii + 1 : n_all - 1;
+          const long long ju = ii >= W ? ii - W : 0, jd = ii + W < n_all ? ii + W : n_all - 1;
+          zc[u] = z[ii]; po[u] = pold[ii];
+          zl[u] = z[jl]; pl[u] = pold[jl]; zr[u] = z[jr]; pr[u] = pold[jr];
+          zu[u] = z[ju]; pu[u] = pold[ju]; zd[u] = z[jd]; pd[u] = pold[jd];
+          sd[u] = __ldg(&Df[ii]); swr[u] = __ldg(&WHf[ii]); swd[u] = __ldg(&WVf[ii]);
+          swl[u] = __ldg(&WHf[jl]); swu[u] = __ldg(&WVf[ju]);
+          sa12[u] = __ldg(&a12f[ii]);
+          yc[u] = y[ii];
+        }
+#pragma unroll
+        for (int u = 0; u < MIX_UA; ++u) {
+          if (!ok[u]) continue;
+          const float2 c = make_float2(zc[u].x + beta * po[u].x, zc[u].y + beta * po[u].y);
+          float2 nl = make_float2(zl[u].x + beta * pl[u].x, zl[u].y + beta * pl[u].y);
+          float2 nr = make_float2(zr[u].x + beta * pr[u].x, zr[u].y + beta * pr[u].y);
+          float2 nu = make_float2(zu[u].x + beta * pu[u].x, zu[u].y + beta * pu[u].y);
+          float2 nd = make_float2(zd[u].x + beta * pd[u].x, zd[u].y + beta * pd[u].y);
+          if (px[u] == 0) nl = c;
+          if (px[u] + 1 >= W) nr = c;
+          if (py[u] == 0) nu = c;
+          if (py[u] + 1 >= H) nd = c;
+          float au = sd[u].x * c.x + sa12[u] * c.y;
+          float av = sa12[u] * c.x + sd[u].y * c.y;
+          au += swr[u].x * (c.x - nr.x); av += swr[u].y * (c.y - nr.y);
+          au += swl[u].x * (c.x - nl.x); av += swl[u].y * (c.y - nl.y);
+          au += swd[u].x * (c.x - nd.x); av += swd[u].y * (c.y - nd.y);
+          au += swu[u].x * (c.x - nu.x); av += swu[u].y * (c.y - nu.y);
+          if (flush) {
+            double2 xc = x[i[u]];
+            x[i[u]] = make_double2(xc.x + ((double)yc[u].x + aprev_d * (double)po[u].x),
+                                   xc.y + ((double)yc[u].y + aprev_d * (double)po[u].y));
+            y[i[u]] = make_float2(0.f, 0.f);
+          } else {
+            y[i[u]] = make_float2(yc[u].x + aprev * po[u].x, yc[u].y + aprev * po[u].y);
+          }
+          pnew[i[u]] = c;
+          Ap[i[u]] = make_float2(au, av);
+          acc += (double)c.x * (double)au + (double)c.y * (double)av;
+        }
+      }
+      block_sum2(acc, dummy, sm_red);
+      if (tid == 0) part_a[(long long)b * G + cta] = acc;
+    }
+    grid.sync();
+    REDUCE_ALL(part_a, (const double *)nullptr, 0)
+    if (tid < B && s_state[tid] == 0) {
+      double pap = s_ta[tid];
+      s_alpha[tid] = pap > 0.0 ? s_rz[tid] / pap : 0.0;      // 0 => breakdown, resolved by the reliable update below
+      s_flush[tid] = 0;
+    }
+    __syncthreads();
+    // ---------------- phase B: r -= alpha Ap, z = M^-1 r, partial r.z and r.r ----------------
+    for (int a = a_first; a <= a_last; ++a) {
+      TILE_RANGE(a)
+      const float alpha = (float)s_alpha[b];
+      double acc_rz = 0.0, acc_rr = 0.0;
+      for (long long t = ta; t < tb; t += MIX_UB) {
+        long long i[MIX_UB]; bool ok[MIX_UB];
+        float2 rc[MIX_UB], ac[MIX_UB];
+        float m11[MIX_UB], m12[MIX_UB], m22[MIX_UB];
+#pragma unroll
+        for (int u = 0; u < MIX_UB; ++u) {
+          int px, py;
+          PIXEL_OF(t + u, px, py, i[u], ok[u])
+          rc[u] = r[i[u]]; ac[u] = Ap[i[u]];
+          m11[u] = __ldg(&Minv[i[u]]); m12[u] = __ldg(&Minv[n_all + i[u]]); m22[u] = __ldg(&Minv[2 * n_all + i[u]]);
+        }
+#pragma unroll
+        for (int u = 0; u < MIX_UB; ++u) {
+          if (!ok[u]) continue;
+          float2 rn = make_float2(rc[u].x - alpha * ac[u].x, rc[u].y - alpha * ac[u].y);
+          float2 zz = make_float2(m11[u] * rn.x + m12[u] * rn.y, m12[u] * rn.x + m22[u] * rn.y);
+          r[i[u]] = rn; z[i[u]] = zz;
+          acc_rz += (double)rn.x * (double)zz.x + (double)rn.y * (double)zz.y;
+          acc_rr += (double)rn.x * (double)rn.x + (double)rn.y * (double)rn.y;
+        }
+      }
+      block_sum2(acc_rz, acc_rr, sm_red);
+      if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
+    }
+    grid.sync();
+    REDUCE_ALL(part_b, part_c, 0)
+    int rel = 0;
+    if (tid < B && s_state[tid] == 0) {
+      const int b = tid;
+      double rz = s_ta[b], rr = s_tb[b], alpha = s_alpha[b];
+      int bad = !(alpha > 0.0) || !(rz > 0.0) || !(rr == rr);
+      rel = bad || rr <= P.tol2 * s_bb[b] || rr < P.delta2 * s_maxr2[b] || k + 1 == P.maxit;
+      if (rel) {
+        s_state[b] = 3; s_bad[b] = bad; s_rzprev[b] = s_rz[b];
+      } else {
+        s_beta[b] = rz / s_rz[b];
+        s_rz[b] = rz;
+      }
+    }
+    if (__syncthreads_or(rel)) {
+      // ---------------- reliable update: r = b - A (x + y + alpha p) in fp64, z = M^-1 r ----------------
+      for (int a = a_first; a <= a_last; ++a) {
+        TILE_RANGE(a)
+        if (s_state[b] != 3) continue;
+        const double alpha = s_alpha[b];
+        double acc_rz = 0.0, acc_rr = 0.0;
+        for (long long t = ta; t < tb; ++t) {
+          int px, py; long long i; bool ok;
+          PIXEL_OF(t, px, py, i, ok)
+          if (!ok) continue;
+          double2 d = mix_reliable_pixel(P, i, px, py, n_all, pnew, alpha);
+          acc_rz += d.x; acc_rr += d.y;
+        }
+        block_sum2(acc_rz, acc_rr, sm_red);
+        if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
+      }
+      grid.sync();
+      REDUCE_ALL(part_b, part_c, 3)
+      int fin = 0;
+      if (tid < B && s_state[tid] == 3) {
+        const int b = tid;
+        double rz = s_ta[b], rr = s_tb[b];
+        int conv = rr <= P.tol2 * s_bb[b];
+        if (conv || s_bad[b] || !(rz > 0.0) || !(rr == rr) || k + 1 == P.maxit) {
+          s_state[b] = 2;
+          fin = 1;
+          if (cta == C_LO(b)) {
+            done_g[b] = conv ? 1 : (k + 1 == P.maxit && !s_bad[b] ? 3 : 2);
+            iters_g[b] = k + 1;
+            relres_g[b] = sqrt(rr / s_bb[b]);
+          }
+        } else {
+          s_state[b] = 0;
+          s_flush[b] = 1;                                  // x += y + alpha_k p_k rides on the next phase A
+          s_maxr2[b] = rr;
+          s_beta[b] = rz / s_rzprev[b];
+          s_rz[b] = rz;
+        }
+      }
+      if (__syncthreads_or(fin)) {
+        // systems that just finished: fold the pending y + alpha p into x (own pixels only), then re-deal the tiles
+        for (int a = a_first; a <= a_last; ++a) {
+          TILE_RANGE(a)
+          if (s_state[b] != 2) continue;
+          const double alpha = s_alpha[b];
+          for (long long t = ta; t < tb; ++t) {
+            int px, py; long long i; bool ok;
+            PIXEL_OF(t, px, py, i, ok)
+            if (!ok) continue;
+            double2 xc = x[i];
+            float2 yc = y[i], pc = pnew[i];
+            x[i] = make_double2(xc.x + ((double)yc.x + alpha * (double)pc.x), xc.y + ((double)yc.y + alpha * (double)pc.y));
+          }
+        }
+        __syncthreads();
+        if (tid < B && s_state[tid] == 2) s_state[tid] = 1;
+        REMAP()
+        n_active = s_nact;
+      }
+    }
+    { float2 *t = pold; pold = pnew; pnew = t; }
+  }
+#undef REMAP
+#undef C_LO
+#undef C_HI
+#undef OWN_RANGE
+#undef REDUCE_ALL
+#undef TILE_RANGE
+#undef PIXEL_OF
+}
+
 // tiny epilogue: fold the per-system outcome of one solve into the running device statistics
 __global__ void pcg_stats_kernel(const int *flags, int B, long long hw, long long *stats) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -363,59 +806,87 @@ size_t pcg_work_bytes(const b200flow_ctx *ctx, int B, int H, int W) {
   return n * (5 * sizeof(double2) + 3 * sizeof(float)) + 4 * (size_t)B * ctx->num_sms * 8 * 8 + 64 * B + 4096;
 }
 
-static int pcg_grid(b200flow_ctx *ctx, int *grid_out) {
-  static int cached_dev = -1, cached = 0;
+static int pcg_grid(b200flow_ctx *ctx, int *grid_out, int *grid_mixed_out) {
+  static int cached_dev = -1, cached = 0, cached_mixed = 0;
   if (cached_dev != ctx->device) {
-    int nb = 0;
+    int nb = 0, nm = 0;
     BF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcg_kernel, PCG_THREADS, 0));
-    if (nb < 1) return set_err(ctx, B200FLOW_ECUDA, "pcg_kernel cannot be made resident");
+    BF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nm, pcg_mixed_kernel, PCG_THREADS, 0));
+    if (nb < 1 || nm < 1) return set_err(ctx, B200FLOW_ECUDA, "pcg kernels cannot be made resident");
     cached = nb * ctx->num_sms;
+    cached_mixed = nm * ctx->num_sms;
     cached_dev = ctx->device;
   }
   *grid_out = cached;
+  *grid_mixed_out = cached_mixed;
   return 0;
 }
 
 int pcg_work_alloc(b200flow_ctx *ctx, int B, int H, int W, PcgWork *w) {
   size_t n = (size_t)B * H * W;
-  int G;
-  BF_TRY(pcg_grid(ctx, &G));
+  int G, Gm;
+  BF_TRY(pcg_grid(ctx, &G, &Gm));
   w->grid = G;
+  w->grid_mixed = Gm;
+  if (Gm > G) G = Gm;
   BF_TRY(arena_alloc(ctx, &w->r, n));
   BF_TRY(arena_alloc(ctx, &w->p, n));
   BF_TRY(arena_alloc(ctx, &w->p2, n));
   BF_TRY(arena_alloc(ctx, &w->z, n));
   BF_TRY(arena_alloc(ctx, &w->Ap, n));
   BF_TRY(arena_alloc(ctx, &w->Minv, 3 * n));
-  BF_TRY(arena_alloc(ctx, &w->partial, (size_t)4 * B * G));
+  BF_TRY(arena_alloc(ctx, &w->partial, (size_t)4 * B * G));   // G = the larger of the two kernels' grids
   BF_TRY(arena_alloc(ctx, &w->scal, (size_t)B));
   BF_TRY(arena_alloc(ctx, &w->flags, (size_t)(1 + 2 * B)));
   return 0;
 }
 
-int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int scalar_jacobi,
+int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                 int *iters_host, double *relres_host, bool sync_results) {
-  PcgParams P;
-  P.sys = sys; P.w = w; P.x = x;
-  P.tol2 = tol * tol;
-  P.maxit = maxit;
-  P.scalar_jacobi = scalar_jacobi;
-  P.tiles_x = (int)cdiv(sys.W, TILE_W);
-  P.tiles_y = (int)cdiv(sys.H, TILE_H);
-  P.tiles_per_sys = P.tiles_x * P.tiles_y;
-  P.total_tiles = (long long)P.tiles_per_sys * sys.B;
-  int G = w.grid;
-  if ((long long)G > P.total_tiles) G = (int)P.total_tiles;
+  const bool mixed = mode == PCG_MODE_MIXED;
+  const int tiles_x = (int)cdiv(sys.W, TILE_W), tiles_y = (int)cdiv(sys.H, TILE_H);
+  const int tiles_per_sys = tiles_x * tiles_y;
+  const long long total_tiles = (long long)tiles_per_sys * sys.B;
+  int G = mixed ? w.grid_mixed : w.grid;
+  if ((long long)G > total_tiles) G = (int)total_tiles;
   if (G < 1) G = 1;
-  P.tiles_per_cta = (int)cdiv(P.total_tiles, G);
-  // keep the number of systems one CTA may touch within the shared-memory table
-  if (P.tiles_per_cta / P.tiles_per_sys + 2 > MAXLOC)
-    return set_err(ctx, B200FLOW_EINVAL, "batch of %d systems of %dx%d is too fine-grained for one solve; split the batch",
-                   sys.B, sys.H, sys.W);
-  P.w.grid = G;
+  const int tiles_per_cta = (int)cdiv(total_tiles, G);
   BF_CUDA(ctx, cudaMemsetAsync(w.flags, 0, sizeof(int) * (1 + 2 * sys.B), ctx->stream));
-  void *args[] = {&P};
-  BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(G), dim3(PCG_THREADS), args, 0, ctx->stream));
+  if (mixed) {
+    if (sys.B > MAXB)
+      return set_err(ctx, B200FLOW_EINVAL, "batch of %d systems exceeds %d per solve; split the batch", sys.B, MAXB);
+    MixParams P;
+    P.sys = sys; P.w = w; P.x = x;
+    P.tol2 = tol * tol;
+    P.delta2 = PCG_RELIABLE_DELTA * PCG_RELIABLE_DELTA;
+    P.maxit = maxit;
+    P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.tiles_per_sys = tiles_per_sys;
+    P.w.grid = G;
+    // the fp32 working set (76 B / pixel) is carved out of the five fp64 vectors (80 B / pixel) of the work area
+    const size_t n = (size_t)sys.B * sys.H * sys.W;
+    P.m.r = reinterpret_cast<float2 *>(w.r);   P.m.z = P.m.r + n;
+    P.m.p = reinterpret_cast<float2 *>(w.p);   P.m.p2 = P.m.p + n;
+    P.m.Ap = reinterpret_cast<float2 *>(w.p2); P.m.y = P.m.Ap + n;
+    P.m.D = reinterpret_cast<float2 *>(w.z);   P.m.WH = P.m.D + n;
+    P.m.WV = reinterpret_cast<float2 *>(w.Ap); P.m.a12 = reinterpret_cast<float *>(P.m.WV + n);
+    void *args[] = {&P};
+    BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_mixed_kernel, dim3(G), dim3(PCG_THREADS), args, 0, ctx->stream));
+  } else {
+    PcgParams P;
+    P.sys = sys; P.w = w; P.x = x;
+    P.tol2 = tol * tol;
+    P.maxit = maxit;
+    P.scalar_jacobi = mode == PCG_MODE_JACOBI_F64;
+    P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.tiles_per_sys = tiles_per_sys;
+    P.total_tiles = total_tiles; P.tiles_per_cta = tiles_per_cta;
+    // keep the number of systems one CTA may touch within the shared-memory table
+    if (P.tiles_per_cta / P.tiles_per_sys + 2 > MAXLOC)
+      return set_err(ctx, B200FLOW_EINVAL, "batch of %d systems of %dx%d is too fine-grained for one solve; split the batch",
+                     sys.B, sys.H, sys.W);
+    P.w.grid = G;
+    void *args[] = {&P};
+    BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(G), dim3(PCG_THREADS), args, 0, ctx->stream));
+  }
   ctx->launches++;
   if (sync_results) {
     std::vector<int> fl(1 + 2 * sys.B);
@@ -436,9 +907,9 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
 }
 
 // pipeline variant: no host sync; outcome accumulated into device statistics
-int k_pcg_solve_async(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int scalar_jacobi,
+int k_pcg_solve_async(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                       long long *stats_dev) {
-  BF_TRY(k_pcg_solve(ctx, sys, w, x, tol, maxit, scalar_jacobi, nullptr, nullptr, false));
+  BF_TRY(k_pcg_solve(ctx, sys, w, x, tol, maxit, mode, nullptr, nullptr, false));
   if (stats_dev) BF_LAUNCH(ctx, pcg_stats_kernel, 1, 32, 0, w.flags, sys.B, (long long)sys.H * sys.W, stats_dev);
   return 0;
 }

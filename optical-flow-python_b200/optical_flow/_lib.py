@@ -71,6 +71,7 @@ _SIGS = {
     "b200flow_median_filter": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "b200flow_detect_occlusion": [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp],
     "b200flow_weighted_median": [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp],
+    "b200flow_debug_pcg_bench": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["b200flow_abi_version", "b200flow_ctx_create", "b200flow_ctx_destroy",
                                 "b200flow_last_error", "b200flow_ctx_set_timing", "b200flow_ctx_sync",

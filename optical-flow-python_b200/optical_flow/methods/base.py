@@ -6,6 +6,10 @@ The public attributes, their defaults and `parse_input_parameter` are those of t
                               stands in for the direct `solver='backslash'` solve.  Measured on RubberWhale 584x388
                               classic+nl-fast against the reference's SuperLU pipeline: 1e-8 -> 3.5e-3 px (a median
                               selection flips), 1e-9 -> 3.6e-5 px; the default 1e-10 keeps a 10x margin on top
+  solver_precision            'mixed' (default): the PCG keeps its Krylov vectors in fp32 and accumulates the solution and
+                              the periodically recomputed TRUE residual in fp64 ("reliable updates"), so convergence
+                              is still declared on the fp64 residual ||b - A x|| <= exact_rtol ||b||; 'fp64': every
+                              vector in fp64 (same criterion, 1.9x the memory traffic)
   last_stats                  dict of solver / launch statistics of the most recent compute_flow call
 """
 import copy
@@ -145,6 +149,7 @@ class BaseOpticalFlow(ABC):
         # additions
         self.exact_rtol = 1e-10
         self.exact_maxiter = 20000
+        self.solver_precision = 'mixed'
         self.last_stats = None
 
     def parse_input_parameter(self, params):
@@ -168,7 +173,10 @@ class BaseOpticalFlow(ABC):
     def _apply_solver(self, P):
         solver = str(self.solver).lower()
         if solver == 'backslash':
-            P.solver, P.tol, P.maxit = 0, float(self.exact_rtol), int(self.exact_maxiter)
+            prec = str(self.solver_precision).lower()
+            if prec not in ('mixed', 'fp64'):
+                raise ValueError(f"Unknown solver_precision: {self.solver_precision}")
+            P.solver, P.tol, P.maxit = (0 if prec == 'mixed' else 2), float(self.exact_rtol), int(self.exact_maxiter)
         elif solver == 'pcg':
             P.solver, P.tol, P.maxit = 1, float(self.pcg_rtol), int(self.pcg_maxiter)
         elif solver == 'sor':
