@@ -246,8 +246,26 @@ __device__ __forceinline__ double wmax(double v) {
   return v;
 }
 
-// fp64 exp kept out of line: it is evaluated NPL times per pixel and inlining it NPL-fold blows the instruction cache
-__device__ __noinline__ double exp_noinline(double x) { return exp(x); }
+// exp(a) for a <= 0, used only as max(exp(a) * occ, 1e-10): arguments below -40 are clamped (their weight is the
+// 1e-10 floor whatever the exponential's value).  Cody-Waite reduction + degree-13 Taylor polynomial on |r| <= ln2/2
+// (truncation error 1.7e-16), coefficients read as constant-bank operands: ~24 instructions against ~46 + call for exp().
+__constant__ double WM_EXPC[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
+                                   1.0 / 362880.0,     1.0 / 40320.0,     1.0 / 5040.0,     1.0 / 720.0,
+                                   1.0 / 120.0,        1.0 / 24.0,        1.0 / 6.0,        0.5};
+__device__ __forceinline__ double exp_nonpos(double a) {
+  a = a > -40.0 ? a : -40.0;
+  const double t = fma(a, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -6.93147180369123816490e-01, a);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = WM_EXPC[0];
+#pragma unroll
+  for (int i = 1; i < 12; ++i) p = fma(p, r, WM_EXPC[i]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // p * 2^k, k in [-58, 0]
+}
 
 // largest double strictly below a finite x
 __device__ __forceinline__ double next_below(double x) {
@@ -257,45 +275,60 @@ __device__ __forceinline__ double next_below(double x) {
   return -4.9406564584124654e-324;
 }
 
-// Weighted median of the NPL x 32 samples x[] with weights w[] held in the warp's registers (all lanes return it).
+// if (x <= p) { s += w; c += 1; }  as DSETP + predicated DADD + predicated IADD (the compiler's own rendering is
+// DSETP + DADD + 2 FSEL + SEL + IADD)
+__device__ __forceinline__ void acc_le(double x, double p, double w, double &s, int &c) {
+  asm("{\n\t.reg .pred q;\n\tsetp.le.f64 q, %2, %3;\n\t@q add.f64 %0, %0, %4;\n\t@q add.s32 %1, %1, 1;\n\t}"
+      : "+d"(s), "+r"(c) : "d"(x), "d"(p), "d"(w));
+}
+
+// Weighted median of the n samples x[] with weights w[] held NPL per lane in the warp's registers (all lanes return it):
 //   t* = min { x_k : S(x_k) >= half },  S(t) = sum of w_k over x_k <= t.
-// "cheap" steps bisect the VALUE range (L, R] using only S(p) and the count n(p) (one fp64 shuffle reduction + one
-// integer REDUX); whenever a step separates nothing (ties / clustered samples) or at most two samples are left, a
-// "snap" pass tightens the bracket to the extreme samples inside it, which also resolves ties exactly.
+// Padding slots hold x = +inf, w = 0, so they are never counted, weighed or bracketed.
+// Stage 1 bisects the VALUE range (L, R] -- invariant S(L) < half <= S(R) -- with steps that only need S(p) and the
+//   count n(p) (one fp64 shuffle reduction + one integer REDUX); a step that separates nothing (ties / clusters) snaps
+//   the bracket to the extreme samples inside it.
+// Stage 2, as soon as at most 32 samples are left inside the bracket (about 4 steps for 225 samples), compacts them one
+//   per lane through `scratch` (warp-private shared memory).
+// Stage 3 keeps bisecting on that one-sample-per-lane set (a step is now ~25 instructions) down to <= 8 survivors and
+//   finishes exactly: every survivor evaluates S at its own value (S(L) + an all-pairs pass over the survivors) and
+//   the smallest one with S >= half is the answer.  The result is always one of the window's samples.
 template <int NPL>
-__device__ __forceinline__ double weighted_select(const double (&x)[NPL], const double (&w)[NPL], double half) {
-  double lo = x[0], hi = x[0];
+__device__ __forceinline__ double weighted_select(const double (&x)[NPL], const double (&w)[NPL], int n, double half,
+                                                  double2 *scratch, int lane) {
+  // value range in fp32 with outward rounding (FMNMX instead of fp64 compare + select pairs)
+  float flo = __double2float_rd(x[0]), fhi = -INFINITY;
 #pragma unroll
-  for (int k = 1; k < NPL; ++k) { lo = x[k] < lo ? x[k] : lo; hi = x[k] > hi ? x[k] : hi; }
+  for (int k = 0; k < NPL; ++k) {
+    flo = fminf(flo, __double2float_rd(x[k]));
+    const float u = __double2float_ru(x[k]);
+    fhi = fmaxf(fhi, u == INFINITY ? -INFINITY : u);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    double t0 = __shfl_xor_sync(0xffffffffu, lo, o), t1 = __shfl_xor_sync(0xffffffffu, hi, o);
-    lo = t0 < lo ? t0 : lo; hi = t1 > hi ? t1 : hi;
+    flo = fminf(flo, __shfl_xor_sync(0xffffffffu, flo, o));
+    fhi = fmaxf(fhi, __shfl_xor_sync(0xffffffffu, fhi, o));
   }
-  if (!(lo < hi)) return hi;
-  double L = next_below(lo), R = hi;       // open-closed value bracket: S(L) < half <= S(R)
-  int nL = 0, nR = 32 * NPL;               // samples <= L, <= R
-  while (true) {
-    bool snap = nR - nL <= 2;
+  double L = next_below((double)flo), R = (double)fhi;   // open-closed value bracket: S(L) = 0 < half <= S(R) = total
+  double SL = 0.0;                                       // S(L)
+  int nL = 0, nR = n;                                    // samples <= L, <= R
+  while (nR - nL > 32) {
+    double p = 0.5 * (L + R);
+    bool snap = !(p > L && p < R);
     if (!snap) {
-      double p = 0.5 * (L + R);
-      if (!(p > L && p < R)) snap = true;
-      else {
-        double s = 0.0;
-        int c = 0;
+      double s = 0.0;
+      int c = 0;
 #pragma unroll
-        for (int k = 0; k < NPL; ++k)
-          if (x[k] <= p) { s += w[k]; c++; }
+      for (int k = 0; k < NPL; ++k) acc_le(x[k], p, w[k], s, c);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (s >= half) { snap = c == nR; R = p; nR = c; }
-        else { snap = c == nL; L = p; nL = c; }
-      }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (s >= half) { snap = c == nR; R = p; nR = c; }
+      else { snap = c == nL; L = p; nL = c; SL = s; }
     }
     if (snap) {
-      // lo = smallest sample > L, hi = largest sample <= R  (both exist: the bracket holds weight)
-      double a = hi, b = lo;
+      // a = smallest sample > L, b = largest sample <= R  (both exist: the bracket holds weight)
+      double a = INFINITY, b = -INFINITY;
 #pragma unroll
       for (int k = 0; k < NPL; ++k) {
         const double xk = x[k];
@@ -307,31 +340,52 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
         double t0 = __shfl_xor_sync(0xffffffffu, a, o), t1 = __shfl_xor_sync(0xffffffffu, b, o);
         a = t0 < a ? t0 : a; b = t1 > b ? t1 : b;
       }
-      lo = a; hi = b;
-      if (!(lo < hi)) return hi;
-      if (nR - nL <= 2) break;             // two distinct samples left: finish below
-      L = next_below(lo); R = hi;
+      if (!(a < b)) return b;              // every sample left in the bracket has the same value
+      L = next_below(a); R = b;            // no sample lies in (old L, new L]: S(L) and the counts are unchanged
     }
   }
-  // final: sample-snapped bisection (at most a couple of steps)
-  while (lo < hi) {
-    double p = 0.5 * (lo + hi);
-    if (!(p < hi)) p = lo;
-    double s = 0.0, bl = lo, ab = hi;
+  // stage 2: compact the survivors (L < x <= R), one per lane
+  int cnt = 0;
+  const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) {
-      const double xk = x[k];
-      if (xk <= p) { s += w[k]; bl = xk > bl ? xk : bl; } else { ab = xk < ab ? xk : ab; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      double t0 = __shfl_xor_sync(0xffffffffu, bl, o), t1 = __shfl_xor_sync(0xffffffffu, ab, o);
-      bl = t0 > bl ? t0 : bl; ab = t1 < ab ? t1 : ab;
-    }
-    if (s >= half) hi = bl; else lo = ab;
+  for (int k = 0; k < NPL; ++k) {
+    const bool in = x[k] > L && x[k] <= R;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) scratch[cnt + __popc(m & lt)] = make_double2(x[k], w[k]);
+    cnt += __popc(m);
   }
-  return hi;
+  __syncwarp();
+  bool valid = lane < cnt;
+  const double2 me = valid ? scratch[lane] : make_double2(INFINITY, 0.0);
+  __syncwarp();
+  // stage 3a: bisection on the compacted set
+  while (cnt > 8) {
+    const double p = 0.5 * (L + R);
+    if (!(p > L && p < R)) break;
+    const bool le = valid && me.x <= p;
+    double s = le ? me.y : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s += SL;
+    const int c = __popc(__ballot_sync(0xffffffffu, le));
+    if (c == 0 || c == cnt) break;         // nothing separated (cluster): let the all-pairs pass sort it out
+    if (s >= half) { R = p; valid = le; cnt = c; }
+    else { L = p; SL = s; valid = valid && !le; cnt -= c; }
+  }
+  // stage 3b: S at every survivor, all pairs
+  double c = SL;
+  for (unsigned m = __ballot_sync(0xffffffffu, valid); m; m &= m - 1) {
+    const int j = __ffs(m) - 1;
+    const double xj = __shfl_sync(0xffffffffu, me.x, j), wj = __shfl_sync(0xffffffffu, me.y, j);
+    if (xj <= me.x) c += wj;
+  }
+  double ans = (valid && c >= half) ? me.x : INFINITY;   // some survivor qualifies: S(largest survivor) = S(R) >= half
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double t = __shfl_xor_sync(0xffffffffu, ans, o);
+    ans = t < ans ? t : ans;
+  }
+  return ans;
 }
 
 template <int NPL, int C>
@@ -346,6 +400,7 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2
   double2 *s_uv = reinterpret_cast<double2 *>(smem);          // [SN]
   double *s_occ = smem + 2 * SN;                               // [SN]
   double *s_col = s_occ + SN;                                  // [C][SN]
+  double2 *s_scr = reinterpret_cast<double2 *>(s_col + C * SN) + 32 * (threadIdx.x >> 5);   // [WM_WARPS][32] compaction scratch
   const int b = blockIdx.z;
   const long long HW = (long long)H * W, off = (long long)b * HW;
   const int x0 = blockIdx.x * WM_TW, y0 = blockIdx.y * WM_TH;
@@ -392,7 +447,7 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2
           double d = s_col[c * SN + q] - cc[c];
           cd += d * d;
         }
-        double wk = exp_noinline(-cd * inv2s2) * s_occ[q];
+        double wk = exp_nonpos(-cd * inv2s2) * s_occ[q];
         w[k] = wk > 1e-10 ? wk : 1e-10;
       }
       tot += w[k];
@@ -400,13 +455,13 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     const double half = tot / 2.0;
-    // padding slots repeat the centre sample with zero weight: they never change S, the minimum or the maximum
+    // padding slots: x = +inf with zero weight (never counted, weighed or bracketed)
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) x[k] = s_uv[qoff[k] >= 0 ? org + qoff[k] : ctr].x;
-    const double mu = weighted_select<NPL>(x, w, half);
+    for (int k = 0; k < NPL; ++k) x[k] = qoff[k] >= 0 ? s_uv[org + qoff[k]].x : INFINITY;
+    const double mu = weighted_select<NPL>(x, w, n, half, s_scr, lane);
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) x[k] = s_uv[qoff[k] >= 0 ? org + qoff[k] : ctr].y;
-    const double mv = weighted_select<NPL>(x, w, half);
+    for (int k = 0; k < NPL; ++k) x[k] = qoff[k] >= 0 ? s_uv[org + qoff[k]].y : INFINITY;
+    const double mv = weighted_select<NPL>(x, w, n, half, s_scr, lane);
     if (lane == 0) {
       long long gi = off + (long long)py * W + px;
       if (base) {
@@ -423,7 +478,7 @@ template <int NPL, int C>
 static int launch_wmedian_c(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color,
                             const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
   int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
-  size_t smem = (size_t)SW * SH * (3 + C) * sizeof(double);
+  size_t smem = (size_t)SW * SH * (3 + C) * sizeof(double) + WM_WARPS * 32 * sizeof(double2);
   if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
   BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
