@@ -479,7 +479,7 @@ int b200flow_weighted_median(b200flow_ctx *ctx, const double *uv, const double *
                              int C, int hsz, double sigma_i, double *out) {
   API_BEGIN(ctx);
   if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
-  if (C < 1 || C > 4) return set_err(ctx, B200FLOW_EINVAL, "weighted median supports 1..4 colour channels, got %d", C);
+  if (C < 1 || C > 3) return set_err(ctx, B200FLOW_EINVAL, "weighted median supports 1..3 colour channels, got %d", C);
   size_t N = (size_t)H * W;
   double *d_uv, *d_col, *d_pl, *d_occ, *d_out;
   BF_TRY(upload(ctx, &d_uv, uv, 2 * N));

@@ -246,16 +246,15 @@ __device__ __forceinline__ double wmax(double v) {
   return v;
 }
 
-// exp(a) for a <= 0, used only as max(exp(a) * occ, 1e-10): arguments below -40 are clamped (their weight is the
-// 1e-10 floor whatever the exponential's value).  Cody-Waite reduction + degree-13 Taylor polynomial on |r| <= ln2/2
+// exp(a) for a <= 0, used only as max(exp(a) * occ, 1e-10): the power-of-two scaling is clamped at 2^-1000 (such weights
+// sit on the 1e-10 floor whatever the exponential's exact value).  Cody-Waite reduction + degree-13 Taylor polynomial on |r| <= ln2/2
 // (truncation error 1.7e-16), coefficients read as constant-bank operands: ~24 instructions against ~46 + call for exp().
 __constant__ double WM_EXPC[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
                                    1.0 / 362880.0,     1.0 / 40320.0,     1.0 / 5040.0,     1.0 / 720.0,
                                    1.0 / 120.0,        1.0 / 24.0,        1.0 / 6.0,        0.5};
 __device__ __forceinline__ double exp_nonpos(double a) {
-  a = a > -40.0 ? a : -40.0;
   const double t = fma(a, 1.4426950408889634, 6755399441055744.0);
-  const int k = __double2loint(t);
+  const int k = max(__double2loint(t), -1000);                // a < -693: any value below the 1e-10 floor will do
   const double kd = t - 6755399441055744.0;
   double r = fma(kd, -6.93147180369123816490e-01, a);
   r = fma(kd, -1.90821492927058770002e-10, r);
@@ -264,7 +263,7 @@ __device__ __forceinline__ double exp_nonpos(double a) {
   for (int i = 1; i < 12; ++i) p = fma(p, r, WM_EXPC[i]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // p * 2^k, k in [-58, 0]
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // p * 2^k, k in [-1000, 0], p in [0.7, 1.42]
 }
 
 // largest double strictly below a finite x
@@ -388,19 +387,20 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
   return ans;
 }
 
-template <int NPL, int C>
+template <int NPL>
 __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2 *__restrict__ cand,
                                                                   const double2 *__restrict__ base,
-                                                                  const double *__restrict__ color,
+                                                                  const double *__restrict__ color, int C,
                                                                   const double *__restrict__ occ, int H, int W, int hsz,
                                                                   double inv2s2, double2 *__restrict__ out) {
   extern __shared__ double smem[];
   const int wsz = 2 * hsz + 1, n = wsz * wsz;
   const int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz, SN = SW * SH;
-  double2 *s_uv = reinterpret_cast<double2 *>(smem);          // [SN]
-  double *s_occ = smem + 2 * SN;                               // [SN]
-  double *s_col = s_occ + SN;                                  // [C][SN]
-  double2 *s_scr = reinterpret_cast<double2 *>(s_col + C * SN) + 32 * (threadIdx.x >> 5);   // [WM_WARPS][32] compaction scratch
+  // staged tile: flow (u, v) and one 32-byte record {colour 0..2 (missing channels 0), occ} per pixel, so that a
+  // sample's weight needs one address and two 16-byte shared loads
+  double2 *s_uv = reinterpret_cast<double2 *>(smem);                      // [SN]
+  double4 *s_cw = reinterpret_cast<double4 *>(smem + 2 * SN);             // [SN]
+  double2 *s_scr = reinterpret_cast<double2 *>(smem + 6 * SN) + 32 * (threadIdx.x >> 5);   // [WM_WARPS][32] compaction scratch
   const int b = blockIdx.z;
   const long long HW = (long long)H * W, off = (long long)b * HW;
   const int x0 = blockIdx.x * WM_TW, y0 = blockIdx.y * WM_TH;
@@ -410,18 +410,20 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2
     long long gi = (long long)gy * W + gx;
     double2 f = cand[off + gi];
     s_uv[t] = make_double2(f.x + 0.0, f.y + 0.0);              // canonicalise -0.0
-    s_occ[t] = occ[off + gi];
-#pragma unroll
-    for (int c = 0; c < C; ++c) s_col[c * SN + t] = color[((long long)b * C + c) * HW + gi];
+    const double *cp = color + (long long)b * C * HW + gi;
+    s_cw[t] = make_double4(cp[0], C > 1 ? cp[HW] : 0.0, C > 2 ? cp[2 * HW] : 0.0, occ[off + gi]);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // window offsets of this lane's NPL samples relative to the window's top-left corner (pixel independent)
+  // window offsets of this lane's NPL samples relative to the window's top-left corner (pixel independent);
+  // padding slots (e >= n) point at the window centre and are given zero weight / x = +inf below
   int qoff[NPL];
+  unsigned vmask = 0u;
 #pragma unroll
   for (int k = 0; k < NPL; ++k) {
     int e = k * 32 + lane;
     int dy = e / wsz, dx = e - dy * wsz;
-    qoff[k] = e < n ? dy * SW + dx : -1;
+    qoff[k] = e < n ? dy * SW + dx : hsz * SW + hsz;
+    vmask |= e < n ? 1u << k : 0u;
   }
   __syncthreads();
   const int py = y0 + warp;
@@ -430,26 +432,19 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2
     const int px = x0 + lx;
     if (px >= W) break;
     const int org = warp * SW + lx;
-    const int ctr = org + hsz * SW + hsz;
-    double cc[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) cc[c] = s_col[c * SN + ctr];
+    const double4 cc = s_cw[org + hsz * SW + hsz];
     double x[NPL], w[NPL];
     double tot = 0.0;
 #pragma unroll
     for (int k = 0; k < NPL; ++k) {
-      w[k] = 0.0;                                  // padding slots: zero weight (and the centre value below)
-      if (qoff[k] >= 0) {
-        int q = org + qoff[k];
-        double cd = 0.0;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          double d = s_col[c * SN + q] - cc[c];
-          cd += d * d;
-        }
-        double wk = exp_nonpos(-cd * inv2s2) * s_occ[q];
-        w[k] = wk > 1e-10 ? wk : 1e-10;
-      }
+      const double4 cq = s_cw[org + qoff[k]];
+      const double d0 = cq.x - cc.x, d1 = cq.y - cc.y, d2 = cq.z - cc.z;
+      double cd = d0 * d0;
+      cd += d1 * d1;
+      cd += d2 * d2;
+      const double wk = exp_nonpos(-cd * inv2s2) * cq.w;
+      // np.maximum(w, 1e-10); padding slots get weight 0
+      w[k] = ((vmask >> k) & 1u) ? (wk > 1e-10 ? wk : 1e-10) : 0.0;
       tot += w[k];
     }
 #pragma unroll
@@ -457,10 +452,10 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2
     const double half = tot / 2.0;
     // padding slots: x = +inf with zero weight (never counted, weighed or bracketed)
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) x[k] = qoff[k] >= 0 ? s_uv[org + qoff[k]].x : INFINITY;
+    for (int k = 0; k < NPL; ++k) x[k] = ((vmask >> k) & 1u) ? s_uv[org + qoff[k]].x : INFINITY;
     const double mu = weighted_select<NPL>(x, w, n, half, s_scr, lane);
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) x[k] = qoff[k] >= 0 ? s_uv[org + qoff[k]].y : INFINITY;
+    for (int k = 0; k < NPL; ++k) x[k] = ((vmask >> k) & 1u) ? s_uv[org + qoff[k]].y : INFINITY;
     const double mv = weighted_select<NPL>(x, w, n, half, s_scr, lane);
     if (lane == 0) {
       long long gi = off + (long long)py * W + px;
@@ -474,34 +469,23 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2
   }
 }
 
-template <int NPL, int C>
-static int launch_wmedian_c(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color,
-                            const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
-  int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
-  size_t smem = (size_t)SW * SH * (3 + C) * sizeof(double) + WM_WARPS * 32 * sizeof(double2);
-  if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
-  BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
-  double inv2s2 = 1.0 / (2.0 * (sigma_i * sigma_i));
-  BF_LAUNCH(ctx, (wmedian_kernel<NPL, C>), grd, WM_WARPS * 32, smem, cand, base, color, occ, H, W, hsz, inv2s2, out);
-  return 0;
-}
-
 template <int NPL>
 static int launch_wmedian(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color, int C,
                           const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
-  switch (C) {
-    case 1: return launch_wmedian_c<NPL, 1>(ctx, cand, base, color, occ, B, H, W, hsz, sigma_i, out);
-    case 2: return launch_wmedian_c<NPL, 2>(ctx, cand, base, color, occ, B, H, W, hsz, sigma_i, out);
-    case 3: return launch_wmedian_c<NPL, 3>(ctx, cand, base, color, occ, B, H, W, hsz, sigma_i, out);
-    default: return launch_wmedian_c<NPL, 4>(ctx, cand, base, color, occ, B, H, W, hsz, sigma_i, out);
-  }
+  int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
+  size_t smem = (size_t)SW * SH * 6 * sizeof(double) + WM_WARPS * 32 * sizeof(double2);
+  if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
+  BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
+  double inv2s2 = 1.0 / (2.0 * (sigma_i * sigma_i));
+  BF_LAUNCH(ctx, (wmedian_kernel<NPL>), grd, WM_WARPS * 32, smem, cand, base, color, C, occ, H, W, hsz, inv2s2, out);
+  return 0;
 }
 
 int k_weighted_median(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color, int C,
                       const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
   if (hsz < 0) return set_err(ctx, B200FLOW_EINVAL, "area_hsz must be >= 0");
-  if (C < 1 || C > 4) return set_err(ctx, B200FLOW_EINVAL, "weighted median supports 1..4 colour channels, got %d", C);
+  if (C < 1 || C > 3) return set_err(ctx, B200FLOW_EINVAL, "weighted median supports 1..3 colour channels, got %d", C);
   int n = (2 * hsz + 1) * (2 * hsz + 1);
   if (n <= 32) return launch_wmedian<1>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
   if (n <= 64) return launch_wmedian<2>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
