@@ -155,6 +155,25 @@ int b200flow_weighted_median(b200flow_ctx*, const double *uv, const double *colo
                              int H, int W, int C, int hsz, double sigma_i, double *out);
 
 
+/* ---- multi-channel frames: `images` is (.., H, W, 2*NC) = NC channels of frame 1 followed by NC channels
+ *      of frame 2, exactly the stack estimate_flow builds for 1-2 channel 3-D inputs (interface.py:46-52) and the drivers
+ *      accept as `self.images`; It / Ix / Iy are (H, W, NC).  The data term averages the IRLS weight and each product
+ *      over the channels (derivatives.py:208-233,265-292; classic_nl.py:330-343; ba.py:254-267; hs.py:176-181); occlusion
+ *      averages |warp - frame 1| (occlusion.py:47-54).  NC = 1 is identical to the entry points above, which forward here. */
+int b200flow_estimate_mc(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int NC, int C,
+                         const double *images, const double *color, const double *init, double *uv_out,
+                         b200flow_stats *stats);
+int b200flow_partial_deriv_mc(b200flow_ctx*, const double *images, const double *uv, int H, int W, int NC, int interp,
+                              const double filt[5], double blend, double *It, double *Ix, double *Iy);
+int b200flow_operator_apply_mc(b200flow_ctx*, const b200flow_params*, double alpha, const double *uv, const double *duv,
+                               const double *It, const double *Ix, const double *Iy, int H, int W, int NC,
+                               const double *x, double *Ax, double *b, double *diag);
+int b200flow_solve_increment_mc(b200flow_ctx*, const b200flow_params*, double alpha, const double *uv, const double *duv,
+                                const double *It, const double *Ix, const double *Iy, int H, int W, int NC,
+                                double *x, int *iters, double *relres);
+int b200flow_detect_occlusion_mc(b200flow_ctx*, const double *uv, const double *images, int H, int W, int NC,
+                                 double sigma_d, double sigma_i, double *occ);
+
 /* ---- diagnostics (bench.py / ncu; no reference counterpart): CUDA-event time of `reps` solves of a synthetic batch of B
  *      random SPD five-point systems (coefficients spanning `decades` decades) run for exactly `iters` iterations */
 int b200flow_debug_pcg_bench(b200flow_ctx*, int B, int H, int W, int solver, int iters, int reps, double decades,

@@ -92,18 +92,19 @@ int b200flow_ctx_num_sms(const b200flow_ctx *ctx) { return ctx ? ctx->num_sms : 
 // ------------------------------------------------------------------------------------------------
 // whole pipeline
 // ------------------------------------------------------------------------------------------------
-static int estimate_dev_impl(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C,
+static int estimate_dev_impl(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int NC, int C,
                              const double *images_dev, const double *color_dev, const double *init_dev,
                              double *uv_out_dev, b200flow_stats *stats) {
   long long HW = (long long)H * W;
   double *gray, *col = nullptr;
-  BF_TRY(arena_alloc(ctx, &gray, (size_t)B * 2 * HW));
-  BF_TRY(k_deinterleave(ctx, images_dev, gray, B, HW, 2));
+  if (NC < 1 || NC > 8) return set_err(ctx, B200FLOW_EINVAL, "channels per frame NC=%d unsupported (1..8)", NC);
+  BF_TRY(arena_alloc(ctx, &gray, (size_t)B * 2 * NC * HW));
+  BF_TRY(k_deinterleave(ctx, images_dev, gray, B, HW, 2 * NC));
   if (color_dev && C > 0) {
     BF_TRY(arena_alloc(ctx, &col, (size_t)B * C * HW));
     BF_TRY(k_deinterleave(ctx, color_dev, col, B, HW, C));
   }
-  return run_pipeline(ctx, p, B, H, W, C, gray, col, reinterpret_cast<const double2 *>(init_dev),
+  return run_pipeline(ctx, p, B, H, W, NC, C, gray, col, reinterpret_cast<const double2 *>(init_dev),
                       reinterpret_cast<double2 *>(uv_out_dev), stats);
 }
 
@@ -112,22 +113,29 @@ int b200flow_estimate_dev(b200flow_ctx *ctx, const b200flow_params *p, int B, in
                           double *uv_out_dev, b200flow_stats *stats) {
   API_BEGIN(ctx);
   if (!images_dev || !uv_out_dev) return set_err(ctx, B200FLOW_EINVAL, "images / uv_out is NULL");
-  BF_TRY(estimate_dev_impl(ctx, p, B, H, W, C, images_dev, color_dev, init_dev, uv_out_dev, stats));
+  BF_TRY(estimate_dev_impl(ctx, p, B, H, W, 1, C, images_dev, color_dev, init_dev, uv_out_dev, stats));
   return 0;
 }
 
 int b200flow_estimate(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C, const double *images,
                       const double *color, const double *init, double *uv_out, b200flow_stats *stats) {
+  return b200flow_estimate_mc(ctx, p, B, H, W, 1, C, images, color, init, uv_out, stats);
+}
+
+int b200flow_estimate_mc(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int NC, int C,
+                         const double *images, const double *color, const double *init, double *uv_out,
+                         b200flow_stats *stats) {
   API_BEGIN(ctx);
   if (!images || !uv_out) return set_err(ctx, B200FLOW_EINVAL, "images / uv_out is NULL");
   if (B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad batch/size B=%d H=%d W=%d", B, H, W);
+  if (NC < 1 || NC > 8) return set_err(ctx, B200FLOW_EINVAL, "channels per frame NC=%d unsupported (1..8)", NC);
   size_t N = (size_t)B * H * W;
   double *d_img, *d_col = nullptr, *d_init = nullptr, *d_out;
-  BF_TRY(upload(ctx, &d_img, images, 2 * N));
+  BF_TRY(upload(ctx, &d_img, images, 2 * NC * N));
   if (color && C > 0) BF_TRY(upload(ctx, &d_col, color, (size_t)C * N));
   if (init) BF_TRY(upload(ctx, &d_init, init, 2 * N));
   BF_TRY(arena_alloc(ctx, &d_out, 2 * N));
-  BF_TRY(estimate_dev_impl(ctx, p, B, H, W, C, d_img, d_col, d_init, d_out, stats));
+  BF_TRY(estimate_dev_impl(ctx, p, B, H, W, NC, C, d_img, d_col, d_init, d_out, stats));
   BF_TRY(download(ctx, uv_out, d_out, 2 * N));
   API_SYNC(ctx);
   return 0;
@@ -145,7 +153,7 @@ static int estimate_rgb8_dev_impl(b200flow_ctx *ctx, const b200flow_params *p, i
   }
   BF_TRY(k_rgb8_to_gray_lab(ctx, rgb1, rgb2, B, HW, gray, lab));
   if (use_color) BF_TRY(k_minmax_scale(ctx, lab, labs, B * 3, HW, 0.0, 255.0));   // each Lab channel separately (interface.py:59-60)
-  return run_pipeline(ctx, p, B, H, W, use_color ? 3 : 0, gray, labs, nullptr, reinterpret_cast<double2 *>(uv_out_dev),
+  return run_pipeline(ctx, p, B, H, W, 1, use_color ? 3 : 0, gray, labs, nullptr, reinterpret_cast<double2 *>(uv_out_dev),
                       stats);
 }
 
@@ -284,32 +292,43 @@ int b200flow_resample_flow(b200flow_ctx *ctx, const double *uv, int h, int w, in
 
 int b200flow_partial_deriv(b200flow_ctx *ctx, const double *images, const double *uv, int H, int W, int interp,
                            const double filt[5], double blend, double *It, double *Ix, double *Iy) {
+  return b200flow_partial_deriv_mc(ctx, images, uv, H, W, 1, interp, filt, blend, It, Ix, Iy);
+}
+
+int b200flow_partial_deriv_mc(b200flow_ctx *ctx, const double *images, const double *uv, int H, int W, int NC, int interp,
+                              const double filt[5], double blend, double *It, double *Ix, double *Iy) {
   API_BEGIN(ctx);
   if (interp < 0 || interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", interp);
   if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
+  if (NC < 1 || NC > 8) return set_err(ctx, B200FLOW_EINVAL, "channels per frame NC=%d unsupported (1..8)", NC);
   size_t N = (size_t)H * W;
-  double *d_img, *d_pl, *d_uv, *I1x, *I1y, *dIt, *dIx, *dIy;
+  double *d_img, *d_pl, *d_uv, *I1x, *I1y, *dIt, *dIx, *dIy, *d_il;
   double4 *src2;
-  BF_TRY(upload(ctx, &d_img, images, 2 * N));
+  BF_TRY(upload(ctx, &d_img, images, 2 * NC * N));
   BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
-  BF_TRY(arena_alloc(ctx, &d_pl, 2 * N));
-  BF_TRY(arena_alloc(ctx, &I1x, N));
-  BF_TRY(arena_alloc(ctx, &I1y, N));
-  BF_TRY(arena_alloc(ctx, &src2, N));
-  BF_TRY(arena_alloc(ctx, &dIt, N));
-  BF_TRY(arena_alloc(ctx, &dIx, N));
-  BF_TRY(arena_alloc(ctx, &dIy, N));
-  BF_TRY(k_deinterleave(ctx, d_img, d_pl, 1, (long long)N, 2));
-  BF_TRY(k_level_prep(ctx, d_pl, d_pl + N, 2 * (long long)N, 1, H, W, interp, filt, I1x, I1y, src2));
+  BF_TRY(arena_alloc(ctx, &d_pl, 2 * NC * N));
+  BF_TRY(arena_alloc(ctx, &I1x, NC * N));
+  BF_TRY(arena_alloc(ctx, &I1y, NC * N));
+  BF_TRY(arena_alloc(ctx, &src2, NC * N));
+  BF_TRY(arena_alloc(ctx, &dIt, NC * N));
+  BF_TRY(arena_alloc(ctx, &dIx, NC * N));
+  BF_TRY(arena_alloc(ctx, &dIy, NC * N));
+  BF_TRY(arena_alloc(ctx, &d_il, 3 * NC * N));
+  BF_TRY(k_deinterleave(ctx, d_img, d_pl, 1, (long long)N, 2 * NC));
+  BF_TRY(k_level_prep(ctx, d_pl, 2 * NC * (long long)N, 1, NC, H, W, interp, filt, I1x, I1y, src2));
   PenaltySet ps;
   memset(&ps, 0, sizeof ps);
   LinSys none;
   memset(&none, 0, sizeof none);
-  BF_TRY(k_warp_assemble(ctx, d_pl, 2 * (long long)N, I1x, I1y, src2, (const double2 *)d_uv, nullptr, 1, H, W, interp,
-                         blend, ps, none, dIt, dIx, dIy));
-  BF_TRY(download(ctx, It, dIt, N));
-  BF_TRY(download(ctx, Ix, dIx, N));
-  BF_TRY(download(ctx, Iy, dIy, N));
+  BF_TRY(k_warp_assemble(ctx, d_pl, 2 * NC * (long long)N, NC, I1x, I1y, src2, (const double2 *)d_uv, nullptr, 1, H, W,
+                         interp, blend, ps, none, dIt, dIx, dIy));
+  // planar [NC][H][W] -> the (H, W, NC) interleaved layout of the reference's arrays
+  BF_TRY(k_interleave(ctx, dIt, d_il, 1, (long long)N, NC));
+  BF_TRY(k_interleave(ctx, dIx, d_il + NC * N, 1, (long long)N, NC));
+  BF_TRY(k_interleave(ctx, dIy, d_il + 2 * NC * N, 1, (long long)N, NC));
+  BF_TRY(download(ctx, It, d_il, NC * N));
+  BF_TRY(download(ctx, Ix, d_il + NC * N, NC * N));
+  BF_TRY(download(ctx, Iy, d_il + 2 * NC * N, NC * N));
   API_SYNC(ctx);
   return 0;
 }
@@ -330,30 +349,45 @@ int b200flow_robust_eval(b200flow_ctx *ctx, b200flow_penalty pen, int d_type, co
 }
 
 static int assemble_host(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv, const double *duv,
-                         const double *It, const double *Ix, const double *Iy, int H, int W, LinSys *sys) {
+                         const double *It, const double *Ix, const double *Iy, int H, int W, int NC, LinSys *sys) {
   if (!p) return set_err(ctx, B200FLOW_EINVAL, "params is NULL");
   if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
   if (p->method != B200FLOW_HS && !(alpha >= 0.0 && alpha <= 1.0))
     return set_err(ctx, B200FLOW_EINVAL, "Invalid GNC alpha: %g", alpha);
+  if (NC < 1 || NC > 8) return set_err(ctx, B200FLOW_EINVAL, "channels per frame NC=%d unsupported (1..8)", NC);
   size_t N = (size_t)H * W;
   double *d_uv, *d_duv = nullptr, *dIt, *dIx, *dIy;
   BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
   if (duv) BF_TRY(upload(ctx, &d_duv, duv, 2 * N));
-  BF_TRY(upload(ctx, &dIt, It, N));
-  BF_TRY(upload(ctx, &dIx, Ix, N));
-  BF_TRY(upload(ctx, &dIy, Iy, N));
+  BF_TRY(upload(ctx, &dIt, It, NC * N));
+  BF_TRY(upload(ctx, &dIx, Ix, NC * N));
+  BF_TRY(upload(ctx, &dIy, Iy, NC * N));
+  if (NC > 1) {     // (H, W, NC) interleaved -> planar
+    double *pl;
+    BF_TRY(arena_alloc(ctx, &pl, 3 * NC * N));
+    BF_TRY(k_deinterleave(ctx, dIt, pl, 1, (long long)N, NC));
+    BF_TRY(k_deinterleave(ctx, dIx, pl + NC * N, 1, (long long)N, NC));
+    BF_TRY(k_deinterleave(ctx, dIy, pl + 2 * NC * N, 1, (long long)N, NC));
+    dIt = pl; dIx = pl + NC * N; dIy = pl + 2 * NC * N;
+  }
   BF_TRY(alloc_linsys(ctx, 1, H, W, sys));
   PenaltySet ps = make_penalty_set(p, alpha);
-  BF_TRY(k_assemble_from_deriv(ctx, dIt, dIx, dIy, (const double2 *)d_uv, (const double2 *)d_duv, 1, H, W, ps, *sys));
+  BF_TRY(k_assemble_from_deriv(ctx, dIt, dIx, dIy, NC, (const double2 *)d_uv, (const double2 *)d_duv, 1, H, W, ps, *sys));
   return 0;
 }
 
 int b200flow_operator_apply(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv,
                             const double *duv, const double *It, const double *Ix, const double *Iy, int H, int W,
                             const double *x, double *Ax, double *b, double *diag) {
+  return b200flow_operator_apply_mc(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, 1, x, Ax, b, diag);
+}
+
+int b200flow_operator_apply_mc(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv,
+                               const double *duv, const double *It, const double *Ix, const double *Iy, int H, int W,
+                               int NC, const double *x, double *Ax, double *b, double *diag) {
   API_BEGIN(ctx);
   LinSys sys;
-  BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, &sys));
+  BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, NC, &sys));
   size_t N = (size_t)H * W;
   double *d_x = nullptr, *d_Ax = nullptr, *d_diag = nullptr;
   if (x && Ax) {
@@ -372,9 +406,15 @@ int b200flow_operator_apply(b200flow_ctx *ctx, const b200flow_params *p, double 
 int b200flow_solve_increment(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv,
                              const double *duv, const double *It, const double *Ix, const double *Iy, int H, int W,
                              double *x, int *iters, double *relres) {
+  return b200flow_solve_increment_mc(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, 1, x, iters, relres);
+}
+
+int b200flow_solve_increment_mc(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv,
+                                const double *duv, const double *It, const double *Ix, const double *Iy, int H, int W,
+                                int NC, double *x, int *iters, double *relres) {
   API_BEGIN(ctx);
   LinSys sys;
-  BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, &sys));
+  BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, NC, &sys));
   if (!(p->tol > 0.0) || p->maxit < 1) return set_err(ctx, B200FLOW_EINVAL, "solver tol/maxit invalid");
   if (p->solver != B200FLOW_SOLVER_EXACT && p->solver != B200FLOW_SOLVER_PCG && p->solver != B200FLOW_SOLVER_EXACT_F64)
     return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
@@ -460,16 +500,22 @@ int b200flow_median_filter(b200flow_ctx *ctx, const double *uv, int H, int W, in
 
 int b200flow_detect_occlusion(b200flow_ctx *ctx, const double *uv, const double *images, int H, int W, double sigma_d,
                               double sigma_i, double *occ) {
+  return b200flow_detect_occlusion_mc(ctx, uv, images, H, W, 1, sigma_d, sigma_i, occ);
+}
+
+int b200flow_detect_occlusion_mc(b200flow_ctx *ctx, const double *uv, const double *images, int H, int W, int NC,
+                                 double sigma_d, double sigma_i, double *occ) {
   API_BEGIN(ctx);
   if (H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad image size");
+  if (NC < 1 || NC > 8) return set_err(ctx, B200FLOW_EINVAL, "channels per frame NC=%d unsupported (1..8)", NC);
   size_t N = (size_t)H * W;
   double *d_uv, *d_img, *d_pl, *d_occ;
   BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
-  BF_TRY(upload(ctx, &d_img, images, 2 * N));
-  BF_TRY(arena_alloc(ctx, &d_pl, 2 * N));
+  BF_TRY(upload(ctx, &d_img, images, 2 * NC * N));
+  BF_TRY(arena_alloc(ctx, &d_pl, 2 * NC * N));
   BF_TRY(arena_alloc(ctx, &d_occ, N));
-  BF_TRY(k_deinterleave(ctx, d_img, d_pl, 1, (long long)N, 2));
-  BF_TRY(k_occlusion(ctx, (const double2 *)d_uv, d_pl, d_pl + N, 2 * (long long)N, 1, H, W, sigma_d, sigma_i, d_occ));
+  BF_TRY(k_deinterleave(ctx, d_img, d_pl, 1, (long long)N, 2 * NC));
+  BF_TRY(k_occlusion(ctx, (const double2 *)d_uv, d_pl, 2 * NC * (long long)N, NC, 1, H, W, sigma_d, sigma_i, d_occ));
   BF_TRY(download(ctx, occ, d_occ, N));
   API_SYNC(ctx);
   return 0;

@@ -170,14 +170,15 @@ int k_hs_norm_gate(b200flow_ctx *ctx, const double2 *x, int B, long long n, int 
 // ------------------------------------------------------------------------------------------------
 // occlusion confidence (occlusion.py:6-56)      bytes/pixel: read uv 16 + im1 8 + im2 8, write 8 = 40
 // ------------------------------------------------------------------------------------------------
-__global__ void occlusion_kernel(const double2 *__restrict__ uv, const double *__restrict__ im1,
-                                 const double *__restrict__ im2, long long bstride, int H, int W, double sigma_d,
-                                 double sigma_i, double *__restrict__ occ) {
+// frames: [B][2*NC][H][W]; multi-channel frames average |warp - frame 1| over the channels (occlusion.py:47-54)
+__global__ void occlusion_kernel(const double2 *__restrict__ uv, const double *__restrict__ frames, long long bstride,
+                                 int NC, int H, int W, double sigma_d, double sigma_i, double *__restrict__ occ) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
-  long long off = (long long)blockIdx.z * H * W;
-  uv += off; im1 += (long long)blockIdx.z * bstride; im2 += (long long)blockIdx.z * bstride;
+  const long long HW = (long long)H * W;
+  long long off = (long long)blockIdx.z * HW;
+  uv += off; frames += (long long)blockIdx.z * bstride;
   long long i = (long long)y * W + x;
   double2 f = uv[i];
   double div = 0.0;
@@ -190,16 +191,21 @@ __global__ void occlusion_kernel(const double2 *__restrict__ uv, const double *_
   int fx = (int)floor(x2), fy = (int)floor(y2);
   double tx = x2 - (double)fx, ty = y2 - (double)fy;
   int x1 = min(fx + 1, W - 1), y1 = min(fy + 1, H - 1);
-  double w2 = (1.0 - ty) * ((1.0 - tx) * im2[(long long)fy * W + fx] + tx * im2[(long long)fy * W + x1]) +
-              ty * ((1.0 - tx) * im2[(long long)y1 * W + fx] + tx * im2[(long long)y1 * W + x1]);
-  double it = fabs(w2 - im1[i]);
+  double it = 0.0;
+  for (int c = 0; c < NC; ++c) {
+    const double *im1 = frames + (long long)c * HW, *im2 = im1 + (long long)NC * HW;
+    double w2 = (1.0 - ty) * ((1.0 - tx) * im2[(long long)fy * W + fx] + tx * im2[(long long)fy * W + x1]) +
+                ty * ((1.0 - tx) * im2[(long long)y1 * W + fx] + tx * im2[(long long)y1 * W + x1]);
+    it += fabs(w2 - im1[i]);
+  }
+  if (NC > 1) it /= (double)NC;
   occ[off + i] = exp(-(div * div) / (2.0 * (sigma_d * sigma_d))) * exp(-(it * it) / (2.0 * (sigma_i * sigma_i)));
 }
 
-int k_occlusion(b200flow_ctx *ctx, const double2 *uv, const double *im1, const double *im2, long long bstride, int B,
+int k_occlusion(b200flow_ctx *ctx, const double2 *uv, const double *frames, long long bstride, int NC, int B,
                 int H, int W, double sigma_d, double sigma_i, double *occ) {
   dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
-  BF_LAUNCH(ctx, occlusion_kernel, grd, blk, 0, uv, im1, im2, bstride, H, W, sigma_d, sigma_i, occ);
+  BF_LAUNCH(ctx, occlusion_kernel, grd, blk, 0, uv, frames, bstride, NC, H, W, sigma_d, sigma_i, occ);
   return 0;
 }
 

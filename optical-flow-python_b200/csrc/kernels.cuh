@@ -53,15 +53,16 @@ int level_size(int n, double ratio);
 int auto_levels(int H, int W, double spacing);
 
 // ---- warp.cu
-// im1/im2 point at the first pair's frames; pair b's frames are bstride doubles further on ([B][2][H][W] layout)
-int k_level_prep(b200flow_ctx *, const double *im1, const double *im2, long long bstride, int B, int H, int W,
+// frames: [B][2*NC][H][W], NC channels of frame 1 then NC channels of frame 2 (bstride = 2*NC*H*W for a dense batch);
+// I1x / I1y / src2 / It / Ix / Iy are [B][NC][H][W]
+int k_level_prep(b200flow_ctx *, const double *frames, long long bstride, int B, int NC, int H, int W,
                  int interp, const double filt[5], double *I1x, double *I1y, double4 *src2);
-int k_warp_assemble(b200flow_ctx *, const double *im1, long long bstride, const double *I1x, const double *I1y,
+int k_warp_assemble(b200flow_ctx *, const double *frames, long long bstride, int NC, const double *I1x, const double *I1y,
                     const double4 *src2,
                     const double2 *uv, const double2 *duv, int B, int H, int W, int interp, double blend,
                     const PenaltySet &ps, LinSys sys, double *It, double *Ix, double *Iy);
 // assemble from given derivative planes (operator_apply / solve_increment entry points, max_linear>1 re-linearisation)
-int k_assemble_from_deriv(b200flow_ctx *, const double *It, const double *Ix, const double *Iy, const double2 *uv,
+int k_assemble_from_deriv(b200flow_ctx *, const double *It, const double *Ix, const double *Iy, int NC, const double2 *uv,
                           const double2 *duv, int B, int H, int W, const PenaltySet &ps, LinSys sys);
 int k_robust_eval(b200flow_ctx *, b200flow_penalty pen, int d_type, const double *x, long long n, double *y);
 
@@ -85,7 +86,7 @@ int k_median_uv(b200flow_ctx *, const double2 *base, const double2 *x, int limit
                 double2 *out, int B, int H, int W, int kh, int kw, int assign_direct);
 int k_clip_add(b200flow_ctx *, const double2 *uv, const double2 *x, int limit_update, const int *active, double2 *out,
                long long n_per_item, int B);
-int k_occlusion(b200flow_ctx *, const double2 *uv, const double *im1, const double *im2, long long bstride, int B,
+int k_occlusion(b200flow_ctx *, const double2 *uv, const double *frames, long long bstride, int NC, int B,
                 int H, int W, double sigma_d, double sigma_i, double *occ);
 int k_sub(b200flow_ctx *, const double2 *a, const double2 *b, double2 *out, long long n);
 // out = base + (wmed(cand) - base) when base != null else wmed(cand)
@@ -94,7 +95,7 @@ int k_weighted_median(b200flow_ctx *, const double2 *cand, const double2 *base, 
 int k_hs_norm_gate(b200flow_ctx *, const double2 *x, int B, long long n, int *active, double *scratch);
 
 // ---- pipeline.cu
-int run_pipeline(b200flow_ctx *, const b200flow_params *p, int B, int H, int W, int C, const double *gray_planar,
+int run_pipeline(b200flow_ctx *, const b200flow_params *p, int B, int H, int W, int NC, int C, const double *gray_planar,
                  const double *color_planar, const double2 *init, double2 *uv_out, b200flow_stats *stats);
 
 }  // namespace bf

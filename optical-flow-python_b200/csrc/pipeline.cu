@@ -84,7 +84,7 @@ int check_params(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
     return set_err(ctx, B200FLOW_EINVAL, "pyramid_spacing %g out of range (1, 8]", p->pyramid_spacing);
   if (p->method != B200FLOW_HS && (!(p->gnc_pyramid_spacing > 1.0) || p->gnc_pyramid_spacing > 8.0))
     return set_err(ctx, B200FLOW_EINVAL, "gnc_pyramid_spacing %g out of range (1, 8]", p->gnc_pyramid_spacing);
-  if (C < 0 || C > 4) return set_err(ctx, B200FLOW_EINVAL, "colour channels C=%d unsupported", C);
+  if (C < 0 || C > 3) return set_err(ctx, B200FLOW_EINVAL, "colour channels C=%d unsupported (0..3)", C);
   if (!(p->tol > 0.0) || p->maxit < 1) return set_err(ctx, B200FLOW_EINVAL, "solver tol/maxit invalid");
   const b200flow_penalty *pens[] = {&p->rho_su[0], &p->rho_su[1], &p->rho_sv[0], &p->rho_sv[1], &p->rho_d,
                                     &p->qua_su[0], &p->qua_su[1], &p->qua_sv[0], &p->qua_sv[1], &p->qua_d};
@@ -120,9 +120,12 @@ int alloc_linsys(b200flow_ctx *ctx, int B, int H, int W, LinSys *s) {
   return 0;
 }
 
-int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C, const double *gray_planar,
+// gray_planar: [B][2*NC][H][W] -- NC channels of frame 1, then NC channels of frame 2 (NC = 1 for gray frames)
+int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int NC, int C, const double *gray_planar,
                  const double *color_planar, const double2 *init, double2 *uv_out, b200flow_stats *stats) {
   BF_TRY(check_params(ctx, p, B, H, W, C));
+  if (NC < 1 || NC > 8) return set_err(ctx, B200FLOW_EINVAL, "channels per frame NC=%d unsupported (1..8)", NC);
+  const int NP = 2 * NC;                                  // image planes per pair
   const long long HW = (long long)H * W;
   const size_t N = (size_t)B * HW;
   const bool hs = p->method == B200FLOW_HS, cnl = p->method == B200FLOW_CLASSICNL;
@@ -139,18 +142,18 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
   // ---- pre-processing: texture or [0,255] scaling (joint over the two frames of a pair) ----
   tm.begin(T_PRE);
   double *pre;
-  BF_TRY(arena_alloc(ctx, &pre, 2 * N));
-  if (p->texture > 0) BF_TRY(k_rof_texture(ctx, gray_planar, pre, B, 2, H, W, p->rof_theta, p->rof_iters, p->alp));
-  else if (p->texture == 0) BF_TRY(k_minmax_scale(ctx, gray_planar, pre, B, 2 * HW, 0.0, 255.0));
-  else BF_CUDA(ctx, cudaMemcpyAsync(pre, gray_planar, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  BF_TRY(arena_alloc(ctx, &pre, NP * N));
+  if (p->texture > 0) BF_TRY(k_rof_texture(ctx, gray_planar, pre, B, NP, H, W, p->rof_theta, p->rof_iters, p->alp));
+  else if (p->texture == 0) BF_TRY(k_minmax_scale(ctx, gray_planar, pre, B, NP * HW, 0.0, 255.0));
+  else BF_CUDA(ctx, cudaMemcpyAsync(pre, gray_planar, NP * N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 
   int levels = (hs || p->auto_level) ? auto_levels(H, W, p->pyramid_spacing) : p->pyramid_levels;
   if (p->pyramid_levels > 0 && !p->auto_level) levels = p->pyramid_levels;
   Pyramid pyr, gpyr, cpyr, gcpyr;
-  BF_TRY(build_pyramid(ctx, pre, 2 * B, H, W, levels, p->pyramid_spacing, &pyr));
+  BF_TRY(build_pyramid(ctx, pre, NP * B, H, W, levels, p->pyramid_spacing, &pyr));
   const bool use_color = cnl && color_planar != nullptr && C > 0;
   if (!hs) {
-    BF_TRY(build_pyramid(ctx, pre, 2 * B, H, W, p->gnc_pyramid_levels, p->gnc_pyramid_spacing, &gpyr));
+    BF_TRY(build_pyramid(ctx, pre, NP * B, H, W, p->gnc_pyramid_levels, p->gnc_pyramid_spacing, &gpyr));
     if (use_color) {
       BF_TRY(build_pyramid(ctx, const_cast<double *>(color_planar), C * B, H, W, levels, p->pyramid_spacing, &cpyr));
       BF_TRY(build_pyramid(ctx, const_cast<double *>(color_planar), C * B, H, W, p->gnc_pyramid_levels,
@@ -170,9 +173,9 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
   BF_TRY(arena_alloc(ctx, &uvA, N));
   BF_TRY(arena_alloc(ctx, &uvB, N));
   BF_TRY(arena_alloc(ctx, &x, N));
-  BF_TRY(arena_alloc(ctx, &I1x, N));
-  BF_TRY(arena_alloc(ctx, &I1y, N));
-  BF_TRY(arena_alloc(ctx, &src2, N));
+  BF_TRY(arena_alloc(ctx, &I1x, NC * N));
+  BF_TRY(arena_alloc(ctx, &I1y, NC * N));
+  BF_TRY(arena_alloc(ctx, &src2, NC * N));
   BF_TRY(alloc_linsys(ctx, B, H, W, &sys));
   BF_TRY(pcg_work_alloc(ctx, B, H, W, &work));
   BF_TRY(arena_alloc(ctx, &dstats, 4));
@@ -187,9 +190,9 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
   }
   if (!hs && p->max_linear > 1) {
     BF_TRY(arena_alloc(ctx, &duv, N));
-    BF_TRY(arena_alloc(ctx, &It, N));
-    BF_TRY(arena_alloc(ctx, &Ix, N));
-    BF_TRY(arena_alloc(ctx, &Iy, N));
+    BF_TRY(arena_alloc(ctx, &It, NC * N));
+    BF_TRY(arena_alloc(ctx, &Ix, NC * N));
+    BF_TRY(arena_alloc(ctx, &Iy, NC * N));
   }
 
   double2 *cur = uvA, *nxt = uvB;
@@ -213,13 +216,13 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
     for (int l = nl - 1; l >= 0; --l) {
       const int h = ip.H[l], w = ip.W[l];
       const long long hw = (long long)h * w;
-      const double *im1 = ip.lv[l], *im2 = ip.lv[l] + hw;
-      const long long bstride = 2 * hw;
+      const double *frames = ip.lv[l];
+      const long long bstride = NP * hw;
       tm.begin(T_WARP);
       BF_TRY(k_resample_flow(ctx, cur, nxt, B, ch, cw, h, w));
       std::swap(cur, nxt);
       ch = h; cw = w;
-      BF_TRY(k_level_prep(ctx, im1, im2, bstride, B, h, w, p->interp, p->deriv_filter, I1x, I1y, src2));
+      BF_TRY(k_level_prep(ctx, frames, bstride, B, NC, h, w, p->interp, p->deriv_filter, I1x, I1y, src2));
       tm.end();
       sys.H = h; sys.W = w;
       if (hs) BF_LAUNCH(ctx, fill_int_kernel, (unsigned)cdiv(B, 128), 128, 0, active, B, 1);
@@ -231,10 +234,10 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
         for (int j = 0; j < nlin; ++j) {
           tm.begin(T_WARP);
           if (j == 0)
-            BF_TRY(k_warp_assemble(ctx, im1, bstride, I1x, I1y, src2, cur, nullptr, B, h, w, p->interp, p->blend, ps, sys,
-                                   nlin > 1 ? It : nullptr, Ix, Iy));
+            BF_TRY(k_warp_assemble(ctx, frames, bstride, NC, I1x, I1y, src2, cur, nullptr, B, h, w, p->interp, p->blend, ps,
+                                   sys, nlin > 1 ? It : nullptr, Ix, Iy));
           else
-            BF_TRY(k_assemble_from_deriv(ctx, It, Ix, Iy, cur, dcur, B, h, w, ps, sys));
+            BF_TRY(k_assemble_from_deriv(ctx, It, Ix, Iy, NC, cur, dcur, B, h, w, ps, sys));
           tm.end();
           tm.begin(T_SOLVE);
           BF_TRY(k_pcg_solve_async(ctx, sys, work, x, p->tol, p->maxit, pcg_mode, dstats));
@@ -266,7 +269,7 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
             }
           } else if (cnl && have_median && use_color) {
             BF_TRY(k_clip_add(ctx, cur, x, p->limit_update, nullptr, cand, hw, B));
-            BF_TRY(k_occlusion(ctx, cand, im1, im2, bstride, B, h, w, p->occ_sigma_d, p->occ_sigma_i, occ));
+            BF_TRY(k_occlusion(ctx, cand, frames, bstride, NC, B, h, w, p->occ_sigma_d, p->occ_sigma_i, occ));
             BF_TRY(k_weighted_median(ctx, cand, cur, cp.lv[l], C, occ, B, h, w, p->area_hsz, p->sigma_i, nxt));
           } else if (have_median) {
             // BA (ba.py:197-201) and Classic+NL without a usable colour image (weighted_median.py:42-47: square mfsz[0])

@@ -78,14 +78,18 @@ int k_robust_eval(b200flow_ctx *ctx, b200flow_penalty pen, int d_type, const dou
 // ------------------------------------------------------------------------------------------------
 struct Filt5 { double h[5]; };
 
-__global__ void level_prep_kernel(const double *__restrict__ im1, const double *__restrict__ im2, long long bstride,
+// frames: [B][2*NC][H][W] (frame-1 channels, then frame-2 channels; pair stride bstride); outputs [B][NC][H][W]
+__global__ void level_prep_kernel(const double *__restrict__ frames, long long bstride, int NC,
                                   int H, int W, int hermite, Filt5 f, double *__restrict__ I1x,
                                   double *__restrict__ I1y, double4 *__restrict__ src2) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
-  long long off = (long long)blockIdx.z * H * W;
-  im1 += (long long)blockIdx.z * bstride; im2 += (long long)blockIdx.z * bstride;
+  const long long HW = (long long)H * W;
+  long long off = (long long)blockIdx.z * HW;
+  const int pb = blockIdx.z / NC, pc = blockIdx.z - pb * NC;
+  const double *im1 = frames + (long long)pb * bstride + (long long)pc * HW;
+  const double *im2 = im1 + (long long)NC * HW;
   int xs[5], ys[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) { xs[k] = reflect_idx(x + k - 2, W); ys[k] = reflect_idx(y + k - 2, H); }
@@ -175,16 +179,16 @@ __global__ void bspline_prefilter_kernel(double4 *__restrict__ c, int H, int W, 
   }
 }
 
-int k_level_prep(b200flow_ctx *ctx, const double *im1, const double *im2, long long bstride, int B, int H, int W,
+int k_level_prep(b200flow_ctx *ctx, const double *frames, long long bstride, int B, int NC, int H, int W,
                  int interp, const double filt[5], double *I1x, double *I1y, double4 *src2) {
   Filt5 f;
   for (int i = 0; i < 5; ++i) f.h[i] = filt[i];
-  dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
-  BF_LAUNCH(ctx, level_prep_kernel, grd, blk, 0, im1, im2, bstride, H, W,
+  dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B * NC);
+  BF_LAUNCH(ctx, level_prep_kernel, grd, blk, 0, frames, bstride, NC, H, W,
             interp == B200FLOW_INTERP_BICUBIC ? 1 : 0, f, I1x, I1y, src2);
   if (interp == B200FLOW_INTERP_CUBIC) {
     // scipy spline_filter: axis 0 (columns) first, then axis 1 (rows)
-    int ncol = B * W, nrow = B * H;
+    int ncol = B * NC * W, nrow = B * NC * H;
     BF_LAUNCH(ctx, bspline_prefilter_kernel, (unsigned)cdiv(ncol, 64), 64, 0, src2, H, W, 0, ncol);
     BF_LAUNCH(ctx, bspline_prefilter_kernel, (unsigned)cdiv(nrow, 64), 64, 0, src2, H, W, 1, nrow);
   }
@@ -327,8 +331,40 @@ __device__ __forceinline__ double blended_data(const PenaltySet &ps, double it_l
   return d;
 }
 
+// data-term part of one pixel's 2x2 block and right-hand side
+struct DataTerm { double a11, a22, a12, bu, bv; };
+
+// single-channel frames (flow_operator's `else` branch, classic_nl.py:344-351)
+__device__ __forceinline__ DataTerm data_term_single(const PenaltySet &ps, Deriv dv, double2 dc) {
+  double it_lin = dv.It + dv.Ix * dc.x + dv.Iy * dc.y;
+  double d = blended_data(ps, it_lin);
+  DataTerm t;
+  t.a11 = d * dv.Ix * dv.Ix; t.a22 = d * dv.Iy * dv.Iy; t.a12 = d * dv.Ix * dv.Iy;
+  t.bu = d * it_lin * dv.Ix; t.bv = d * it_lin * dv.Iy;
+  return t;
+}
+
+// multi-channel frames: the IRLS weight and every product are AVERAGED over the channels separately and only then
+// multiplied (classic_nl.py:330-343, ba.py:254-267, hs.py:176-181)
+struct DataAccum {
+  double sd = 0.0, ix2 = 0.0, iy2 = 0.0, ixy = 0.0, itx = 0.0, ity = 0.0;
+  __device__ __forceinline__ void add(const PenaltySet &ps, Deriv dv, double2 dc) {
+    double it_lin = dv.It + dv.Ix * dc.x + dv.Iy * dc.y;
+    sd += blended_data(ps, it_lin);
+    ix2 += dv.Ix * dv.Ix; iy2 += dv.Iy * dv.Iy; ixy += dv.Ix * dv.Iy;
+    itx += it_lin * dv.Ix; ity += it_lin * dv.Iy;
+  }
+  __device__ __forceinline__ DataTerm finish(int NC) const {
+    double n = (double)NC, d = sd / n;
+    DataTerm t;
+    t.a11 = d * (ix2 / n); t.a22 = d * (iy2 / n); t.a12 = d * (ixy / n);
+    t.bu = d * (itx / n); t.bv = d * (ity / n);
+    return t;
+  }
+};
+
 __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const double2 *__restrict__ uv,
-                                               const double2 *__restrict__ duv, int H, int W, int x, int y, Deriv dv,
+                                               const double2 *__restrict__ duv, int H, int W, int x, int y, DataTerm dt,
                                                const LinSys &sys, long long gi) {
   long long i = (long long)y * W + x;
   double2 c0 = uv[i];                                       // uv (for the rhs Laplacian)
@@ -370,18 +406,16 @@ __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const doubl
     lu += wu * (c0.x - n0.x);
     lv += wv * (c0.y - n0.y);
   }
-  double it_lin = dv.It + dv.Ix * dc.x + dv.Iy * dc.y;
-  double d = blended_data(ps, it_lin);
-  sys.D[gi] = make_double2(d * dv.Ix * dv.Ix, d * dv.Iy * dv.Iy);
-  sys.a12[gi] = d * dv.Ix * dv.Iy;
+  sys.D[gi] = make_double2(dt.a11, dt.a22);
+  sys.a12[gi] = dt.a12;
   sys.WH[gi] = make_double2(whu, whv);
   sys.WV[gi] = make_double2(wvu, wvv);
-  sys.rhs[gi] = make_double2(-lu - d * it_lin * dv.Ix, -lv - d * it_lin * dv.Iy);
+  sys.rhs[gi] = make_double2(-lu - dt.bu, -lv - dt.bv);
 }
 
-// algorithmic bytes per pixel: read uv 16 + im1,I1x,I1y 24 + gathered source 32,
-// write D 16 + a12 8 + WH 16 + WV 16 + rhs 16  = 144 B
-__global__ void __launch_bounds__(256) warp_assemble_kernel(const double *__restrict__ im1, long long bstride,
+// algorithmic bytes per pixel, single-channel frames: read uv 16 + im1,I1x,I1y 24 + gathered source 32,
+// write D 16 + a12 8 + WH 16 + WV 16 + rhs 16  = 144 B   (NC channels: 88 + 56 NC)
+__global__ void __launch_bounds__(256) warp_assemble_kernel(const double *__restrict__ frames, long long bstride, int NC,
                                      const double *__restrict__ I1x,
                                      const double *__restrict__ I1y, const double4 *__restrict__ src2,
                                      const double2 *__restrict__ uv, const double2 *__restrict__ duv, int H, int W,
@@ -390,42 +424,75 @@ __global__ void __launch_bounds__(256) warp_assemble_kernel(const double *__rest
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
-  long long off = (long long)blockIdx.z * H * W;
+  const long long HW = (long long)H * W;
+  long long off = (long long)blockIdx.z * HW;
   long long i = (long long)y * W + x;
-  Deriv dv = pixel_deriv(im1 + (long long)blockIdx.z * bstride, I1x + off, I1y + off, src2 + off, H, W, x, y,
-                         uv[off + i], interp, blend);
-  if (It) { It[off + i] = dv.It; Ix[off + i] = dv.Ix; Iy[off + i] = dv.Iy; }
-  if (do_assemble) assemble_pixel(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, dv, sys, off + i);
+  const double2 f = uv[off + i];
+  const double2 dc = duv ? duv[off + i] : make_double2(0.0, 0.0);
+  DataTerm dt;
+  if (NC == 1) {
+    Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride, I1x + off, I1y + off, src2 + off, H, W, x, y, f,
+                           interp, blend);
+    if (It) { It[off + i] = dv.It; Ix[off + i] = dv.Ix; Iy[off + i] = dv.Iy; }
+    dt = data_term_single(ps, dv, dc);
+  } else {
+    DataAccum acc;
+    for (int c = 0; c < NC; ++c) {
+      const long long coff = ((long long)blockIdx.z * NC + c) * HW;
+      Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride + (long long)c * HW, I1x + coff, I1y + coff,
+                             src2 + coff, H, W, x, y, f, interp, blend);
+      if (It) { It[coff + i] = dv.It; Ix[coff + i] = dv.Ix; Iy[coff + i] = dv.Iy; }
+      acc.add(ps, dv, dc);
+    }
+    dt = acc.finish(NC);
+  }
+  if (do_assemble) assemble_pixel(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, dt, sys, off + i);
 }
 
+// It, Ix, Iy: [B][NC][H][W]
 __global__ void __launch_bounds__(256) assemble_from_deriv_kernel(const double *__restrict__ It, const double *__restrict__ Ix,
-                                           const double *__restrict__ Iy, const double2 *__restrict__ uv,
+                                           const double *__restrict__ Iy, int NC, const double2 *__restrict__ uv,
                                            const double2 *__restrict__ duv, int H, int W, PenaltySet ps, LinSys sys) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
-  long long off = (long long)blockIdx.z * H * W;
+  const long long HW = (long long)H * W;
+  long long off = (long long)blockIdx.z * HW;
   long long i = (long long)y * W + x;
-  Deriv dv;
-  dv.It = It[off + i]; dv.Ix = Ix[off + i]; dv.Iy = Iy[off + i];
-  assemble_pixel(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, dv, sys, off + i);
+  const double2 dc = duv ? duv[off + i] : make_double2(0.0, 0.0);
+  DataTerm dt;
+  if (NC == 1) {
+    Deriv dv;
+    dv.It = It[off + i]; dv.Ix = Ix[off + i]; dv.Iy = Iy[off + i];
+    dt = data_term_single(ps, dv, dc);
+  } else {
+    DataAccum acc;
+    for (int c = 0; c < NC; ++c) {
+      const long long j = ((long long)blockIdx.z * NC + c) * HW + i;
+      Deriv dv;
+      dv.It = It[j]; dv.Ix = Ix[j]; dv.Iy = Iy[j];
+      acc.add(ps, dv, dc);
+    }
+    dt = acc.finish(NC);
+  }
+  assemble_pixel(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, dt, sys, off + i);
 }
 
-int k_warp_assemble(b200flow_ctx *ctx, const double *im1, long long bstride, const double *I1x, const double *I1y,
+int k_warp_assemble(b200flow_ctx *ctx, const double *frames, long long bstride, int NC, const double *I1x, const double *I1y,
                     const double4 *src2, const double2 *uv, const double2 *duv, int B, int H, int W, int interp, double blend,
                     const PenaltySet &ps, LinSys sys, double *It, double *Ix, double *Iy) {
   if (interp < 0 || interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", interp);
   dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
   int do_assemble = sys.D != nullptr;
-  BF_LAUNCH(ctx, warp_assemble_kernel, grd, blk, 0, im1, bstride, I1x, I1y, src2, uv, duv, H, W, interp, blend, ps,
+  BF_LAUNCH(ctx, warp_assemble_kernel, grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp, blend, ps,
             sys, It, Ix, Iy, do_assemble);
   return 0;
 }
 
-int k_assemble_from_deriv(b200flow_ctx *ctx, const double *It, const double *Ix, const double *Iy, const double2 *uv,
+int k_assemble_from_deriv(b200flow_ctx *ctx, const double *It, const double *Ix, const double *Iy, int NC, const double2 *uv,
                           const double2 *duv, int B, int H, int W, const PenaltySet &ps, LinSys sys) {
   dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
-  BF_LAUNCH(ctx, assemble_from_deriv_kernel, grd, blk, 0, It, Ix, Iy, uv, duv, H, W, ps, sys);
+  BF_LAUNCH(ctx, assemble_from_deriv_kernel, grd, blk, 0, It, Ix, Iy, NC, uv, duv, H, W, ps, sys);
   return 0;
 }
 

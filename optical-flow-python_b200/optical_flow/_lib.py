@@ -71,6 +71,14 @@ _SIGS = {
     "b200flow_median_filter": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "b200flow_detect_occlusion": [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp],
     "b200flow_weighted_median": [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp],
+    "b200flow_estimate_mc": [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
+                             C.POINTER(Stats)],
+    "b200flow_partial_deriv_mc": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _vp, _vp, _vp],
+    "b200flow_operator_apply_mc": [C.POINTER(Params), C.c_double, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
+                                   _vp, _vp, _vp, _vp],
+    "b200flow_solve_increment_mc": [C.POINTER(Params), C.c_double, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
+                                    _vp, _ip, _dp],
+    "b200flow_detect_occlusion_mc": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp],
     "b200flow_debug_pcg_bench": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["b200flow_abi_version", "b200flow_ctx_create", "b200flow_ctx_destroy",

@@ -36,6 +36,7 @@ class FlowOperator:
         self.terms = terms                      # list of (coefficient, driver object carrying rho_* / lambda_)
         H, W = uv.shape[:2]
         self.hw = (H, W)
+        self.nc = 1 if np.ndim(It) == 2 else It.shape[2]     # channels per frame (derivative planes are (H, W, nc))
         self.shape = (2 * H * W, 2 * H * W)
         self.dtype = np.dtype(float)
         self._b = None
@@ -60,9 +61,9 @@ class FlowOperator:
         for coef, obj in self.terms:
             P = obj._c_params(single=True)
             ax, b, d = np.empty((H, W, 2)), np.empty((H, W, 2)), np.empty((H, W, 2))
-            ctx.call("b200flow_operator_apply", P, 0.0, _lib.ptr(self._uv), _lib.ptr(self._duv), _lib.ptr(self._It),
-                     _lib.ptr(self._Ix), _lib.ptr(self._Iy), H, W, _lib.ptr(x), _lib.ptr(ax) if x is not None else None,
-                     _lib.ptr(b), _lib.ptr(d))
+            ctx.call("b200flow_operator_apply_mc", P, 0.0, _lib.ptr(self._uv), _lib.ptr(self._duv), _lib.ptr(self._It),
+                     _lib.ptr(self._Ix), _lib.ptr(self._Iy), H, W, self.nc, _lib.ptr(x),
+                     _lib.ptr(ax) if x is not None else None, _lib.ptr(b), _lib.ptr(d))
             tot_ax = tot_ax + coef * ax
             tot_b = tot_b + coef * b
             tot_d = tot_d + coef * d
@@ -101,9 +102,9 @@ class FlowOperator:
         x = np.empty((H, W, 2))
         iters = _lib.C.c_int(0)
         rel = _lib.C.c_double(0.0)
-        _lib.default_context().call("b200flow_solve_increment", P, float(alpha), _lib.ptr(self._uv), _lib.ptr(self._duv),
-                                    _lib.ptr(self._It), _lib.ptr(self._Ix), _lib.ptr(self._Iy), H, W, _lib.ptr(x),
-                                    _lib.C.byref(iters), _lib.C.byref(rel), allow_noconv=True)
+        _lib.default_context().call("b200flow_solve_increment_mc", P, float(alpha), _lib.ptr(self._uv),
+                                    _lib.ptr(self._duv), _lib.ptr(self._It), _lib.ptr(self._Ix), _lib.ptr(self._Iy), H, W,
+                                    self.nc, _lib.ptr(x), _lib.C.byref(iters), _lib.C.byref(rel), allow_noconv=True)
         owner.last_stats = {"pcg_iters": iters.value, "relres": rel.value}
         return x
 
@@ -247,10 +248,10 @@ class BaseOpticalFlow(ABC):
     def _run(self, P, images, color, init):
         """One b200flow_estimate call for a single pair."""
         images = _lib.f64(images)
-        if images.ndim != 3 or images.shape[2] != 2:
-            raise NotImplementedError("images must be an (H, W, 2) gray frame pair; the multi-channel colour data term "
-                                      "is not built yet (SURVEY.md section 8f rank 1)")
+        if images.ndim != 3 or images.shape[2] < 2 or images.shape[2] % 2:
+            raise ValueError("images must be (H, W, 2C): C channels of frame 1 followed by C channels of frame 2")
         H, W = images.shape[:2]
+        nc = images.shape[2] // 2
         Cn = 0
         if color is not None:
             color = _lib.f64(color)
@@ -259,8 +260,8 @@ class BaseOpticalFlow(ABC):
         uv = np.empty((H, W, 2))
         st = _lib.Stats()
         ctx = _lib.default_context()
-        ctx.call("b200flow_estimate", P, 1, H, W, Cn, _lib.ptr(images), _lib.ptr(color), _lib.ptr(init), _lib.ptr(uv),
-                 _lib.C.byref(st))
+        ctx.call("b200flow_estimate_mc", P, 1, H, W, nc, Cn, _lib.ptr(images), _lib.ptr(color), _lib.ptr(init),
+                 _lib.ptr(uv), _lib.C.byref(st))
         self.last_stats = st.as_dict()
         return uv
 

@@ -389,9 +389,16 @@ def bilinear_eval_nan(img, y0, x0):
 
 
 def partial_deriv(images, uv, interp="cubic", h=DERIV5, blend=0.5):
-    """derivatives.py:148-296, single-channel frames: warp frame 2 by uv, It = warp - frame 1,
+    """derivatives.py:148-296: warp frame 2 by uv, It = warp - frame 1,
     Ix/Iy = blend*warped-derivative + (1-blend)*frame-1 derivative, zero where out of bounds.
-    'bi-cubic' = Hermite (OOB rule floor(x)+1 > W, App. A.4); 'cubic' = B-spline, 'bi-linear'."""
+    'bi-cubic' = Hermite (OOB rule floor(x)+1 > W, App. A.4); 'cubic' = B-spline, 'bi-linear'.
+    images (H,W,2) -> (H,W) planes; images (H,W,2C), C > 1 (frame-1 channels then frame-2 channels,
+    derivatives.py:171-173) -> (H,W,C) planes, every channel treated independently (:208-233, :265-292)."""
+    nc = images.shape[2] // 2
+    if nc > 1:
+        outs = [partial_deriv(np.stack([images[:, :, c], images[:, :, nc + c]], axis=2), uv, interp, h, blend)
+                for c in range(nc)]
+        return tuple(np.stack([o[k] for o in outs], axis=2) for k in range(3))
     im1, im2 = images[:, :, 0], images[:, :, 1]
     H, W = im1.shape
     xg, yg = np.meshgrid(np.arange(1, W + 1, dtype=float), np.arange(1, H + 1, dtype=float))
@@ -505,7 +512,11 @@ def assemble(uv, duv, It, Ix, Iy, spec, alpha):
     lam, lam_q, qua_su, qua_sv, qua_d) where qua_* are the quadratic stand-ins."""
     u = uv[:, :, 0] + duv[:, :, 0]
     v = uv[:, :, 1] + duv[:, :, 1]
-    itl = It + Ix * duv[:, :, 0] + Iy * duv[:, :, 1]
+    multi = It.ndim == 3
+    if multi:    # classic_nl.py:330-343 / ba.py:254-267: weights and products are averaged over the channels
+        itl = It + Ix * duv[:, :, 0:1] + Iy * duv[:, :, 1:2]
+    else:
+        itl = It + Ix * duv[:, :, 0] + Iy * duv[:, :, 1]
     parts = []
     if alpha > 0:
         parts.append((alpha, spec["qua_su"], spec["qua_sv"], spec["qua_d"], spec["lam_q"]))
@@ -517,26 +528,37 @@ def assemble(uv, duv, It, Ix, Iy, spec, alpha):
         wuh, wuv = wuh + wgt * h_, wuv + wgt * v_
         h_, v_ = edge_weights(v, sv[0], sv[1], lam)
         wvh, wvv = wvh + wgt * h_, wvv + wgt * v_
-        d = d + wgt * penalty(pd[0], pd[1], 2, itl)
-    sys = dict(a11=d * Ix * Ix, a12=d * Ix * Iy, a22=d * Iy * Iy, wuh=wuh, wuv=wuv, wvh=wvh, wvv=wvv)
-    sys["bu"] = -graph_laplacian(wuh, wuv, uv[:, :, 0]) - d * itl * Ix
-    sys["bv"] = -graph_laplacian(wvh, wvv, uv[:, :, 1]) - d * itl * Iy
+        pw = penalty(pd[0], pd[1], 2, itl)
+        d = d + wgt * (pw.mean(axis=2) if multi else pw)
+    if multi:
+        ix2, ixy, iy2 = (Ix * Ix).mean(axis=2), (Ix * Iy).mean(axis=2), (Iy * Iy).mean(axis=2)
+        itx, ity = (itl * Ix).mean(axis=2), (itl * Iy).mean(axis=2)
+    else:
+        ix2, ixy, iy2, itx, ity = Ix * Ix, Ix * Iy, Iy * Iy, itl * Ix, itl * Iy
+    sys = dict(a11=d * ix2, a12=d * ixy, a22=d * iy2, wuh=wuh, wuv=wuv, wvh=wvh, wvv=wvv)
+    sys["bu"] = -graph_laplacian(wuh, wuv, uv[:, :, 0]) - d * itx
+    sys["bv"] = -graph_laplacian(wvh, wvv, uv[:, :, 1]) - d * ity
     return sys
 
 
 def assemble_hs(uv, It, Ix, Iy, lam, sigmaD2=1.0, sigmaS2=1.0):
     """hs.py:144-203: d = 1/sigmaD2, unit edge weights scaled by lambda/sigmaS2 (replicate-boundary
     5-point Laplacian == Neumann graph Laplacian)."""
-    H, W = It.shape
+    H, W = It.shape[:2]
     w = lam / sigmaS2
     wh = np.full((H, W), w)
     wh[:, -1] = 0
     wv = np.full((H, W), w)
     wv[-1, :] = 0
     d = 1.0 / sigmaD2
-    sys = dict(a11=d * Ix * Ix, a12=d * Ix * Iy, a22=d * Iy * Iy, wuh=wh, wuv=wv, wvh=wh, wvv=wv)
-    sys["bu"] = -graph_laplacian(wh, wv, uv[:, :, 0]) - d * It * Ix
-    sys["bv"] = -graph_laplacian(wh, wv, uv[:, :, 1]) - d * It * Iy
+    if It.ndim == 3:     # hs.py:176-181: channel means of the products
+        ix2, ixy, iy2 = (Ix * Ix).mean(axis=2), (Ix * Iy).mean(axis=2), (Iy * Iy).mean(axis=2)
+        itx, ity = (It * Ix).mean(axis=2), (It * Iy).mean(axis=2)
+    else:
+        ix2, ixy, iy2, itx, ity = Ix * Ix, Ix * Iy, Iy * Iy, It * Ix, It * Iy
+    sys = dict(a11=d * ix2, a12=d * ixy, a22=d * iy2, wuh=wh, wuv=wv, wvh=wh, wvv=wv)
+    sys["bu"] = -graph_laplacian(wh, wv, uv[:, :, 0]) - d * itx
+    sys["bv"] = -graph_laplacian(wh, wv, uv[:, :, 1]) - d * ity
     return sys
 
 
@@ -619,7 +641,7 @@ def detect_occlusion(uv, images, sigma_d=0.3, sigma_i=20.0):
     div = np.zeros_like(u)
     div[:, 1:] += u[:, 1:] - u[:, :-1]
     div[1:, :] += v[1:, :] - v[:-1, :]
-    im1, im2 = images[:, :, 0], images[:, :, 1]
+    nc = images.shape[2] // 2
     yy, xx = np.mgrid[0:H, 0:W].astype(float)
     x2 = np.clip(xx + u, 0, W - 1)      # map_coordinates mode='nearest' == clamp the coordinate
     y2 = np.clip(yy + v, 0, H - 1)
@@ -628,8 +650,13 @@ def detect_occlusion(uv, images, sigma_d=0.3, sigma_i=20.0):
     tx, ty = x2 - fx, y2 - fy
     x1 = np.minimum(fx + 1, W - 1)
     y1 = np.minimum(fy + 1, H - 1)
-    w2 = (1 - ty) * ((1 - tx) * im2[fy, fx] + tx * im2[fy, x1]) + ty * ((1 - tx) * im2[y1, fx] + tx * im2[y1, x1])
-    it = np.abs(w2 - im1)
+    it = np.zeros((H, W))
+    for c in range(nc):                 # occlusion.py:47-54: mean over the channels of |warp - frame 1|
+        im1, im2 = images[:, :, c], images[:, :, nc + c]
+        w2 = (1 - ty) * ((1 - tx) * im2[fy, fx] + tx * im2[fy, x1]) + ty * ((1 - tx) * im2[y1, fx] + tx * im2[y1, x1])
+        it += np.abs(w2 - im1)
+    if nc > 1:
+        it /= nc
     return np.exp(-div ** 2 / (2 * sigma_d ** 2)) * np.exp(-it ** 2 / (2 * sigma_i ** 2))
 
 
@@ -829,6 +856,8 @@ def estimate_flow(im1, im2, method="classic+nl-fast", params=None, trace=None):
                 p[k] = v
     if im1.ndim == 3 and im1.shape[2] >= 3:
         images = np.stack([rgb2gray(im1), rgb2gray(im2)], axis=2)
+    elif im1.ndim == 3:                 # 1-2 channel stacks are concatenated (interface.py:46-52)
+        images = np.concatenate([im1, im2], axis=2)
     else:
         images = np.stack([im1, im2], axis=2)
     color = None

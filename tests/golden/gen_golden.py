@@ -14,6 +14,7 @@ Files written (tests/golden/):
   systems_<cls>.npz   flow_operator A@probe, b, diag, spsolve(x) for HS / BA / Classic+NL at alpha 1, .5, 0
   e2e_<preset>.npz    estimate_flow() final uv on a 64x80 RubberWhale crop, every in-scope preset
   tape_<preset>.npz   teacher-forcing tape (uv at the start of selected warp iterations + outputs)
+  multichannel.npz    two-channel frames: channel-mean data term, occlusion, ROF, end-to-end flows
   rubberwhale_full.npz (--full) estimate_flow(RubberWhale, 'classic+nl-fast') final uv + AAE/AEPE
   rubberwhale_10_11.npz the two RGB frames + .flo ground truth as uint8 / float32 arrays (fixture data)
 """
@@ -322,6 +323,49 @@ def gen_tape(im1, im2, name, params=None, tagsuffix=""):
     save("tape_%s%s.npz" % (name.replace("+", "p"), tagsuffix), **out)
 
 
+def gen_multichannel(im1, im2):
+    """Two-channel frames (R, G of the RubberWhale crop): estimate_flow concatenates them into a (H, W, 4) image stack
+    (interface.py:46-52) and every data-term quantity becomes a channel mean (derivatives.py:208-233,265-292;
+    classic_nl.py:330-343; ba.py:254-267; hs.py:176-181; occlusion.py:47-54)."""
+    rng = np.random.default_rng(7)
+    c1, c2 = im1[CROP][:, :, :2].astype(float).copy(), im2[CROP][:, :, :2].astype(float).copy()
+    H, W = c1.shape[:2]
+    images = np.concatenate([c1, c2], axis=2)
+    res = {"c1": c1, "c2": c2}
+    tex = structure_texture_decomposition_rof(images, 1.0 / 8, 100, 0.95)
+    res["rof_100"] = tex
+    res["scale_0_255"] = scale_image(images, 0, 255)
+    uv = smooth_flow(rng, H, W, 2.0) + 0.02 * rng.standard_normal((H, W, 2))
+    uv[:6, :, 0] -= 4.0           # drive some samples out of bounds
+    res["uv"] = uv
+    h = np.array([1, -8, 0, 8, -1]) / 12.0
+    for tag, interp in (("bicubic", "bi-cubic"), ("cubic", "cubic"), ("bilinear", "bi-linear")):
+        It, Ix, Iy = partial_deriv(tex, uv, interp, h, 0.5)
+        res["pd_%s_It" % tag], res["pd_%s_Ix" % tag], res["pd_%s_Iy" % tag] = It, Ix, Iy
+    res["occ"] = detect_occlusion(uv, tex)
+    probe = rng.standard_normal(2 * H * W)
+    res["probe"] = probe.reshape((H, W, 2), order="F")
+    duv = 0.1 * smooth_flow(rng, H, W, 1.0)
+    res["duv"] = duv
+    for tag, preset in (("cnl", "classic+nl"), ("ba", "ba"), ("hs", "hs")):
+        ope = _configure(preset)
+        ope.images = tex
+        if preset == "hs":
+            A, b, _, _ = ope.flow_operator(uv)
+        else:
+            It, Ix, Iy = partial_deriv(tex, uv, ope.interpolation_method, h, 0.5)
+            A, b, _, _ = ope.flow_operator(uv, duv, It, Ix, Iy)
+        res[tag + "_Ap"] = (A @ probe).reshape((H, W, 2), order="F")
+        res[tag + "_b"] = b.reshape((H, W, 2), order="F")
+        res[tag + "_x"] = ope._solve_linear_system(A, b, uv.shape)
+    for preset, params in (("hs-brightness", None), ("hs", None), ("ba-brightness", {"max_iters": 3}),
+                           ("classic+nl-fast", None)):
+        t0 = time.time()
+        res["e2e_" + preset] = quiet(estimate_flow, c1, c2, preset, params)
+        print("  multichannel %s: %.1f s" % (preset, time.time() - t0))
+    save("multichannel.npz", **res)
+
+
 def gen_full(im1, im2, tu, tv):
     t0 = time.time()
     uv = quiet(estimate_flow, im1, im2, "classic+nl-fast")
@@ -348,6 +392,8 @@ def main():
         gen_tape(im1, im2, "classic++", {"max_iters": 3}, "_mi3")
         gen_tape(im1, im2, "hs-brightness")
         gen_tape(im1, im2, "ba", {"max_iters": 2}, "_mi2")
+    if args.only in (None, "multichannel"):
+        gen_multichannel(im1, im2)
     if args.full or args.only == "full":
         gen_full(im1, im2, tu, tv)
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import flow_oracle as fo
-from conftest import assert_close, load_golden
+from conftest import assert_close, load_golden, maxabs
 
 TOL = 1e-11      # relative to O(1..255) data: summation-order noise only
 
@@ -145,3 +145,41 @@ def test_unknown_names():
         fo.preset("classic-x")
     with pytest.raises(ValueError):
         fo.partial_deriv(np.zeros((8, 8, 2)), np.zeros((8, 8, 2)), "nearest")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi-channel frames: goldens from the live reference on two-channel inputs
+# ---------------------------------------------------------------------------------------------------------------
+def test_multichannel_oracle_stages():
+    import flow_oracle as fo
+    g = load_golden("multichannel.npz")
+    tex, uv = g["rof_100"], g["uv"]
+    images = np.concatenate([g["c1"], g["c2"]], axis=2)
+    assert maxabs(fo.rof_texture(images), tex) <= 1e-12
+    for tag, interp in (("bicubic", "bi-cubic"), ("cubic", "cubic"), ("bilinear", "bi-linear")):
+        It, Ix, Iy = fo.partial_deriv(tex, uv, interp)
+        assert It.shape == tex.shape[:2] + (2,)
+        for got, key in ((It, "It"), (Ix, "Ix"), (Iy, "Iy")):
+            assert maxabs(got, g["pd_%s_%s" % (tag, key)]) <= 1e-11, (tag, key)
+    assert maxabs(fo.detect_occlusion(uv, tex), g["occ"]) <= 1e-13
+
+
+def test_multichannel_oracle_systems_and_e2e():
+    import flow_oracle as fo
+    g = load_golden("multichannel.npz")
+    tex, uv = g["rof_100"], g["uv"]
+
+    def rel(a, b):
+        return np.abs(a - b).max() / np.abs(b).max()
+    for tag, preset in (("cnl", "classic+nl"), ("ba", "ba")):
+        p = fo.preset(preset)
+        It, Ix, Iy = fo.partial_deriv(tex, uv, p["interp"])
+        sys_ = fo.assemble(uv, g["duv"], It, Ix, Iy, fo._spec(p), 0.0)
+        assert rel(fo.apply_operator(sys_, g["probe"]), g[tag + "_Ap"]) <= 1e-10
+        assert rel(np.stack([sys_["bu"], sys_["bv"]], 2), g[tag + "_b"]) <= 1e-10
+    It, Ix, Iy = fo.partial_deriv(tex, uv, "cubic")
+    sys_ = fo.assemble_hs(uv, It, Ix, Iy, fo.preset("hs")["lam"])
+    assert rel(fo.apply_operator(sys_, g["probe"]), g["hs_Ap"]) <= 1e-12
+    for preset, params in (("hs-brightness", None), ("ba-brightness", {"max_iters": 3}), ("classic+nl-fast", None)):
+        got = fo.estimate_flow(g["c1"], g["c2"], preset, params)
+        assert maxabs(got, g["e2e_" + preset]) <= 1e-4, preset
