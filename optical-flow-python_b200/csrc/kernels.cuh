@@ -72,7 +72,8 @@ int pcg_work_alloc(b200flow_ctx *, int B, int H, int W, PcgWork *w);
 // mode: how `solver` of b200flow_params maps onto the two persistent kernels
 enum { PCG_MODE_MIXED = 0,        // block-Jacobi PCG, fp32 Krylov vectors + fp64 reliable updates (B200FLOW_SOLVER_EXACT)
        PCG_MODE_JACOBI_F64 = 1,   // scalar-Jacobi all-fp64 PCG: the reference's own 'pcg' mode (B200FLOW_SOLVER_PCG)
-       PCG_MODE_BLOCK_F64 = 2 };  // block-Jacobi all-fp64 PCG (B200FLOW_SOLVER_EXACT_F64)
+       PCG_MODE_BLOCK_F64 = 2,    // block-Jacobi all-fp64 PCG (B200FLOW_SOLVER_EXACT_F64)
+       PCG_MODE_SOR = 3 };        // the reference's legacy lexicographic SOR, omega 1.9 (B200FLOW_SOLVER_SOR)
 inline int pcg_mode_of(int solver) { return solver; }
 int k_pcg_solve(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                 int *iters_host /*[B] or null*/, double *relres_host /*[B] or null*/, bool sync_results);

@@ -78,7 +78,7 @@ int check_params(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
   if (B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad batch/size B=%d H=%d W=%d", B, H, W);
   if (p->method < 0 || p->method > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown method %d", p->method);
   if (p->interp < 0 || p->interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", p->interp);
-  if (p->solver != B200FLOW_SOLVER_EXACT && p->solver != B200FLOW_SOLVER_PCG && p->solver != B200FLOW_SOLVER_EXACT_F64)
+  if (p->solver < B200FLOW_SOLVER_EXACT || p->solver > B200FLOW_SOLVER_SOR)
     return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
   if (!(p->pyramid_spacing > 1.0) || p->pyramid_spacing > 8.0)
     return set_err(ctx, B200FLOW_EINVAL, "pyramid_spacing %g out of range (1, 8]", p->pyramid_spacing);

@@ -785,6 +785,88 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
 #undef PIXEL_OF
 }
 
+// ------------------------------------------------------------------------------------------------
+// Legacy solver='sor' (base.py:138-172): Gauss-Seidel SOR, omega 1.9, in the reference's unknown order (all u
+// column-major, then all v column-major), from x = 0, until ||x - x_old|| < tol ||x|| or max_iters sweeps.
+// A cell (y, x) depends only on the already-updated cells (y-1, x) and (y, x-1) of its own component, so the cells of
+// one anti-diagonal x + y = d are independent: one CTA per system sweeps the H + W - 1 anti-diagonals in order, which
+// reproduces the reference's LEXICOGRAPHIC iterates (and therefore its stopping sweep) instead of the different
+// iterates a red-black ordering would give.  Latency-bound by design (one block barrier per anti-diagonal); this is
+// the reference's approximate legacy mode, kept for `params={'solver': 'sor'}`, not a fast path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) sor_kernel(LinSys S, double2 *x2, double omega, double tol, int max_iters,
+                                                   int *flags, double *relres_g) {
+  const int b = blockIdx.x, B = S.B, H = S.H, W = S.W;
+  const long long HW = (long long)H * W, base = (long long)b * HW;
+  double *x = reinterpret_cast<double *>(x2);
+  __shared__ double red[2][32];
+  __shared__ int s_stop;
+  for (long long i = threadIdx.x; i < HW; i += blockDim.x) x2[base + i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  int it = 0;
+  double rel = 0.0;
+  for (; it < max_iters; ++it) {
+    double dx2 = 0.0, xx2 = 0.0;
+    for (int comp = 0; comp < 2; ++comp) {
+      for (int d = 0; d < H + W - 1; ++d) {
+        const int y_lo = d - W + 1 > 0 ? d - W + 1 : 0, y_hi = d < H - 1 ? d : H - 1;
+        for (int c = threadIdx.x; c <= y_hi - y_lo; c += blockDim.x) {
+          const int y = y_lo + c, xq = d - y;
+          const long long i = base + (long long)y * W + xq;
+          const double2 dd = S.D[i], wr = S.WH[i], wd = S.WV[i];
+          const double2 wl = xq > 0 ? S.WH[i - 1] : make_double2(0.0, 0.0);
+          const double2 wu = y > 0 ? S.WV[i - W] : make_double2(0.0, 0.0);
+          const double a = comp ? dd.y : dd.x, kr = comp ? wr.y : wr.x, kd = comp ? wd.y : wd.x;
+          const double kl = comp ? wl.y : wl.x, ku = comp ? wu.y : wu.x;
+          const double f_old = x[2 * i + comp], other = x[2 * i + (1 - comp)];
+          double sig = S.a12[i] * other;
+          if (xq > 0) sig -= kl * x[2 * (i - 1) + comp];
+          if (y > 0) sig -= ku * x[2 * (i - W) + comp];
+          if (y + 1 < H) sig -= kd * x[2 * (i + W) + comp];
+          if (xq + 1 < W) sig -= kr * x[2 * (i + 1) + comp];
+          const double dg = a + (((kr + kd) + kl) + ku);
+          double f_new = f_old;
+          if (fabs(dg) >= 1e-15) {
+            const double rhs = comp ? S.rhs[i].y : S.rhs[i].x;
+            f_new = (1.0 - omega) * f_old + omega * (rhs - sig) / dg;
+            x[2 * i + comp] = f_new;
+          }
+          dx2 += (f_new - f_old) * (f_new - f_old);
+          xx2 += f_new * f_new;
+        }
+        __syncthreads();
+      }
+    }
+    // ||x - x_old|| and ||x|| over the system
+    dx2 = warp_sum(dx2);
+    xx2 = warp_sum(xx2);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = dx2; red[1][w] = xx2; }
+    __syncthreads();
+    if (w == 0) {
+      const int nw = (blockDim.x + 31) >> 5;
+      dx2 = l < nw ? red[0][l] : 0.0;
+      xx2 = l < nw ? red[1][l] : 0.0;
+      dx2 = warp_sum(dx2);
+      xx2 = warp_sum(xx2);
+      if (l == 0) {
+        s_stop = sqrt(dx2) < tol * sqrt(xx2);
+        red[0][0] = xx2 > 0.0 ? sqrt(dx2 / xx2) : 0.0;
+      }
+    }
+    __syncthreads();
+    rel = red[0][0];
+    const int stop = s_stop;
+    __syncthreads();
+    if (stop) { ++it; break; }
+  }
+  if (threadIdx.x == 0) {
+    flags[1 + b] = it < max_iters || rel < tol ? 1 : 3;
+    flags[1 + B + b] = it;
+    relres_g[b] = rel;
+  }
+}
+
 // tiny epilogue: fold the per-system outcome of one solve into the running device statistics
 __global__ void pcg_stats_kernel(const int *flags, int B, long long hw, long long *stats) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -852,7 +934,11 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
   if (G < 1) G = 1;
   const int tiles_per_cta = (int)cdiv(total_tiles, G);
   BF_CUDA(ctx, cudaMemsetAsync(w.flags, 0, sizeof(int) * (1 + 2 * sys.B), ctx->stream));
-  if (mixed) {
+  if (mode == PCG_MODE_SOR) {
+    int len = sys.H < sys.W ? sys.H : sys.W;
+    int threads = len >= 1024 ? 1024 : ((len + 31) / 32) * 32;
+    BF_LAUNCH(ctx, sor_kernel, sys.B, threads, 0, sys, x, 1.9, tol, maxit, w.flags, w.scal);
+  } else if (mixed) {
     if (sys.B > MAXB)
       return set_err(ctx, B200FLOW_EINVAL, "batch of %d systems exceeds %d per solve; split the batch", sys.B, MAXB);
     MixParams P;
@@ -887,7 +973,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     void *args[] = {&P};
     BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(G), dim3(PCG_THREADS), args, 0, ctx->stream));
   }
-  ctx->launches++;
+  if (mode != PCG_MODE_SOR) ctx->launches++;
   if (sync_results) {
     std::vector<int> fl(1 + 2 * sys.B);
     std::vector<double> rr(sys.B);
@@ -900,7 +986,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
       if (relres_host) relres_host[b] = rr[b];
       if (fl[1 + b] != 1) rc = B200FLOW_ENOCONV;
     }
-    if (rc) set_err(ctx, rc, "PCG stopped before reaching tol=%g (maxit=%d)", tol, maxit);
+    if (rc) set_err(ctx, rc, "%s stopped before reaching tol=%g (maxit=%d)", mode == PCG_MODE_SOR ? "SOR" : "PCG", tol, maxit);
     return rc;
   }
   return 0;

@@ -64,7 +64,8 @@ class FlowOperator:
             ctx.call("b200flow_operator_apply_mc", P, 0.0, _lib.ptr(self._uv), _lib.ptr(self._duv), _lib.ptr(self._It),
                      _lib.ptr(self._Ix), _lib.ptr(self._Iy), H, W, self.nc, _lib.ptr(x),
                      _lib.ptr(ax) if x is not None else None, _lib.ptr(b), _lib.ptr(d))
-            tot_ax = tot_ax + coef * ax
+            if x is not None:
+                tot_ax = tot_ax + coef * ax
             tot_b = tot_b + coef * b
             tot_d = tot_d + coef * d
         return tot_ax, tot_b, tot_d
@@ -180,9 +181,8 @@ class BaseOpticalFlow(ABC):
             P.solver, P.tol, P.maxit = (0 if prec == 'mixed' else 2), float(self.exact_rtol), int(self.exact_maxiter)
         elif solver == 'pcg':
             P.solver, P.tol, P.maxit = 1, float(self.pcg_rtol), int(self.pcg_maxiter)
-        elif solver == 'sor':
-            raise NotImplementedError("solver='sor' (lexicographic SOR, omega 1.9) is not built yet; use 'backslash' "
-                                      "(exact-grade PCG) or 'pcg'")
+        elif solver == 'sor':      # base.py:109-110: _sor_solve(A, b, 1.9, self.sor_max_iters, 1e-2)
+            P.solver, P.tol, P.maxit = 3, 1e-2, int(self.sor_max_iters)
         else:
             raise ValueError(f"Unknown solver: {self.solver}")
 

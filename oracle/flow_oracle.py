@@ -597,9 +597,50 @@ def to_sparse(sys):
                         [c, block(sys["a22"], sys["wvh"], sys["wvv"])]]).tocsc()
 
 
-def solve_system(sys, solver="backslash", rtol=1e-3, maxiter=200):
+def sor_solve(sys, omega=1.9, max_iters=10000, tol=1e-2):
+    """_sor_solve (base.py:138-172): Gauss-Seidel SOR in the reference's unknown order -- all u column-major, then
+    all v column-major -- from x = 0, stopping when ||x - x_old|| < tol ||x||.  A cell (y, x) only depends on the
+    already-updated cells (y-1, x) and (y, x-1) of its own component, so the cells of one anti-diagonal x + y = d are
+    independent: sweeping the anti-diagonals in order reproduces the lexicographic iterates (up to the rounding of
+    the row dot product) while staying vectorised."""
+    H, W = sys["a11"].shape
+    diag = operator_diag(sys)
+    xs = np.zeros((H, W, 2))
+    comps = ((0, sys["wuh"], sys["wuv"], sys["bu"]), (1, sys["wvh"], sys["wvv"], sys["bv"]))
+    waves = []
+    for d in range(H + W - 1):
+        ys = np.arange(max(0, d - W + 1), min(H - 1, d) + 1)
+        waves.append((ys, d - ys))
+    for it in range(max_iters):
+        old = xs.copy()
+        for k, wh, wv, b in comps:
+            f = xs[:, :, k]
+            other = xs[:, :, 1 - k]
+            dg = diag[:, :, k]
+            for ys, xx in waves:
+                sig = sys["a12"][ys, xx] * other[ys, xx]
+                m = xx > 0
+                sig[m] -= wh[ys[m], xx[m] - 1] * f[ys[m], xx[m] - 1]
+                m = ys > 0
+                sig[m] -= wv[ys[m] - 1, xx[m]] * f[ys[m] - 1, xx[m]]
+                m = ys + 1 < H
+                sig[m] -= wv[ys[m], xx[m]] * f[ys[m] + 1, xx[m]]
+                m = xx + 1 < W
+                sig[m] -= wh[ys[m], xx[m]] * f[ys[m], xx[m] + 1]
+                dd = dg[ys, xx]
+                ok = np.abs(dd) >= 1e-15
+                new = (1 - omega) * f[ys, xx] + omega * (b[ys, xx] - sig) / np.where(ok, dd, 1.0)
+                f[ys, xx] = np.where(ok, new, f[ys, xx])
+        if np.linalg.norm(xs - old) < tol * np.linalg.norm(xs):
+            break
+    return xs
+
+
+def solve_system(sys, solver="backslash", rtol=1e-3, maxiter=200, sor_max_iters=10000):
     """_solve_linear_system (base.py:87-114): 'backslash' = SuperLU direct solve (reference default);
-    'pcg' = scipy cg with Jacobi preconditioner (base.py:116-136)."""
+    'pcg' = scipy cg with Jacobi preconditioner (base.py:116-136); 'sor' = sor_solve above."""
+    if solver == "sor":
+        return sor_solve(sys, 1.9, sor_max_iters, 1e-2)
     H, W = sys["a11"].shape
     A = to_sparse(sys)
     b = np.concatenate([sys["bu"].ravel(), sys["bv"].ravel()])
@@ -761,7 +802,7 @@ def _preprocess(p, images):
 
 
 def _solve(p, sys):
-    return solve_system(sys, p["solver"], p["pcg_rtol"], p["pcg_maxiter"])
+    return solve_system(sys, p["solver"], p["pcg_rtol"], p["pcg_maxiter"], p.get("sor_max_iters", 10000))
 
 
 def flow_base_gnc(p, spec, images, color, uv, alpha, trace=None):

@@ -15,6 +15,7 @@ Files written (tests/golden/):
   e2e_<preset>.npz    estimate_flow() final uv on a 64x80 RubberWhale crop, every in-scope preset
   tape_<preset>.npz   teacher-forcing tape (uv at the start of selected warp iterations + outputs)
   multichannel.npz    two-channel frames: channel-mean data term, occlusion, ROF, end-to-end flows
+  sor.npz             legacy solver='sor' results (tiny windows: the reference's SOR is a per-row Python loop)
   rubberwhale_full.npz (--full) estimate_flow(RubberWhale, 'classic+nl-fast') final uv + AAE/AEPE
   rubberwhale_10_11.npz the two RGB frames + .flo ground truth as uint8 / float32 arrays (fixture data)
 """
@@ -366,6 +367,41 @@ def gen_multichannel(im1, im2):
     save("multichannel.npz", **res)
 
 
+def gen_sor(im1, im2, stages):
+    """Legacy solver='sor' (lexicographic SOR, omega 1.9, tol 1e-2, base.py:138-172): systems on a 24x32 window and
+    end-to-end flows on a 32x40 window (the reference's per-row Python loop is too slow for more)."""
+    rng = np.random.default_rng(5)
+    sl = (slice(10, 34), slice(20, 52))
+    tex, gray = stages["rof_100"][sl], stages["scale_0_255"][sl]
+    H, W = tex.shape[:2]
+    uv = smooth_flow(rng, H, W, 1.5) + 0.02 * rng.standard_normal((H, W, 2))
+    h = np.array([1, -8, 0, 8, -1]) / 12.0
+    res = {"tex": tex, "gray": gray, "uv": uv}
+    ope = _configure("hs-brightness")
+    ope.images = gray
+    ope.solver = "sor"
+    A, b, _, _ = ope.flow_operator(uv)
+    res["hs_x"] = ope._solve_linear_system(A, b, uv.shape)
+    for tag, preset in (("cnl", "classic+nl"), ("ba", "ba")):
+        ope = _configure(preset)
+        ope.images = tex
+        ope.solver = "sor"
+        It, Ix, Iy = partial_deriv(tex, uv, ope.interpolation_method, h, 0.5)
+        res[tag + "_It"], res[tag + "_Ix"], res[tag + "_Iy"] = It, Ix, Iy
+        A, b, _, _ = ope.flow_operator(uv, np.zeros_like(uv), It, Ix, Iy)
+        t0 = time.time()
+        res[tag + "_x"] = ope._solve_linear_system(A, b, uv.shape)
+        print("  sor %s system: %.1f s" % (tag, time.time() - t0))
+    c = (slice(160, 192), slice(240, 280))
+    c1, c2 = im1[c].copy(), im2[c].copy()
+    res["rgb1"], res["rgb2"] = c1.astype(np.uint8), c2.astype(np.uint8)
+    for preset, params in (("hs-brightness", {"solver": "sor"}), ("ba-brightness", {"solver": "sor", "max_iters": 2})):
+        t0 = time.time()
+        res["e2e_" + preset] = quiet(estimate_flow, c1, c2, preset, params)
+        print("  sor e2e %s: %.1f s" % (preset, time.time() - t0))
+    save("sor.npz", **res)
+
+
 def gen_full(im1, im2, tu, tv):
     t0 = time.time()
     uv = quiet(estimate_flow, im1, im2, "classic+nl-fast")
@@ -394,6 +430,8 @@ def main():
         gen_tape(im1, im2, "ba", {"max_iters": 2}, "_mi2")
     if args.only in (None, "multichannel"):
         gen_multichannel(im1, im2)
+    if args.only in (None, "sor"):
+        gen_sor(im1, im2, dict(np.load(os.path.join(HERE, "stages.npz"))))
     if args.full or args.only == "full":
         gen_full(im1, im2, tu, tv)
 

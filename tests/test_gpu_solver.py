@@ -4,7 +4,7 @@ recorded at the reference's own call sites for HS / BA / Classic+NL / classic++ 
 import numpy as np
 import pytest
 
-from conftest import assert_close
+from conftest import assert_close, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -105,3 +105,44 @@ def test_pcg_determinism_and_batch(systems, precision):
     x1 = ope._solve_linear_system(A, b, uv.shape)
     x2 = ope._solve_linear_system(A, b, uv.shape)
     np.testing.assert_array_equal(x1, x2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's own approximate solver modes
+# ---------------------------------------------------------------------------------------------------------------
+def test_reference_pcg_mode_e2e(stages):
+    """params={'solver': 'pcg'}: scipy cg with the Jacobi preconditioner, rtol 1e-3, maxiter 200 (base.py:116-136).
+    Approximate by design (0.14 px off the direct solve on this crop), but the SAME approximation as the reference's."""
+    from optical_flow import estimate_flow
+    g = load_golden("e2e_classicpnl-fast.npz")
+    uv = estimate_flow(stages["rgb1"].astype(float), stages["rgb2"].astype(float), "classic+nl-fast", {"solver": "pcg"})
+    assert_close(uv, g["uv_pcg_default"], 1e-5, "solver='pcg' end to end vs the reference's solver='pcg'")
+    assert np.abs(uv - g["uv"]).max() > 1e-2          # and it really is the approximate mode, not the exact one
+
+
+@pytest.mark.parametrize("tag,preset", [("hs", "hs-brightness"), ("cnl", "classic+nl"), ("ba", "ba")])
+def test_sor_system(tag, preset):
+    """solver='sor': lexicographic SOR (omega 1.9, tol 1e-2) swept along anti-diagonals reproduces the reference's
+    iterates, hence its (unconverged, approximate) answer."""
+    from optical_flow import load_of_method
+    g = load_golden("sor.npz")
+    ope = load_of_method(preset)
+    ope.solver = "sor"
+    uv = g["uv"]
+    if tag == "hs":
+        ope.images = g["gray"]
+        A, b, _, _ = ope.flow_operator(uv)
+    else:
+        ope.images = g["tex"]
+        A, b, _, _ = ope.flow_operator(uv, np.zeros_like(uv), g[tag + "_It"], g[tag + "_Ix"], g[tag + "_Iy"])
+    x = ope._solve_linear_system(A, b, uv.shape)
+    assert_close(x, g[tag + "_x"], 1e-9, "solver='sor' %s system vs the reference's SOR" % tag)
+
+
+@pytest.mark.parametrize("preset,params", [("hs-brightness", {"solver": "sor"}),
+                                           ("ba-brightness", {"solver": "sor", "max_iters": 2})])
+def test_sor_e2e(preset, params):
+    from optical_flow import estimate_flow
+    g = load_golden("sor.npz")
+    uv = estimate_flow(g["rgb1"].astype(float), g["rgb2"].astype(float), preset, params)
+    assert_close(uv, g["e2e_" + preset], 1e-3, "solver='sor' estimate_flow(%s)" % preset)

@@ -183,3 +183,16 @@ def test_multichannel_oracle_systems_and_e2e():
     for preset, params in (("hs-brightness", None), ("ba-brightness", {"max_iters": 3}), ("classic+nl-fast", None)):
         got = fo.estimate_flow(g["c1"], g["c2"], preset, params)
         assert maxabs(got, g["e2e_" + preset]) <= 1e-4, preset
+
+
+def test_sor_oracle_vs_reference():
+    """Anti-diagonal (wavefront) SOR == the reference's lexicographic per-row loop (base.py:138-172)."""
+    import flow_oracle as fo
+    g = load_golden("sor.npz")
+    uv = g["uv"]
+    It, Ix, Iy = fo.partial_deriv(g["gray"], uv, "cubic")
+    assert maxabs(fo.sor_solve(fo.assemble_hs(uv, It, Ix, Iy, 10.0)), g["hs_x"]) <= 1e-11
+    for tag, preset in (("cnl", "classic+nl"), ("ba", "ba")):
+        p = fo.preset(preset)
+        s = fo.assemble(uv, np.zeros_like(uv), g[tag + "_It"], g[tag + "_Ix"], g[tag + "_Iy"], fo._spec(p), 0.0)
+        assert maxabs(fo.sor_solve(s), g[tag + "_x"]) <= 1e-12
