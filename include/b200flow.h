@@ -176,6 +176,17 @@ int b200flow_solve_increment_mc(b200flow_ctx*, const b200flow_params*, double al
 int b200flow_detect_occlusion_mc(b200flow_ctx*, const double *uv, const double *images, int H, int W, int NC,
                                  double sigma_d, double sigma_i, double *occ);
 
+/* ---- evaluation / export edges, batched over B flow fields (B,H,W,2):
+ *      flow_error   evaluation/metrics.py:5-53 flow_angular_error: result[b] = {AAE deg, std(AE), AEPE, #known pixels};
+ *                   pixels whose ground truth is >= 1e9 in magnitude are skipped, `border` pixels are cropped on every side
+ *      flow_to_color viz/flow_color.py:5-107: Middlebury colour wheel, rgb (B,H,W,3) uint8; max_flow <= 0: per-item maximum
+ *      flow_to_flo  io/flo_io.py:46-63 write_flo: out[b] = the 12 + 8*H*W bytes of the .flo file of item b */
+int b200flow_flow_error(b200flow_ctx*, const double *uv, const double *gt, int B, int H, int W, int border, double *result);
+int b200flow_flow_error_dev(b200flow_ctx*, const double *uv_dev, const double *gt_dev, int B, int H, int W, int border,
+                            double *result /* host */);
+int b200flow_flow_to_color(b200flow_ctx*, const double *uv, int B, int H, int W, double max_flow, unsigned char *rgb);
+int b200flow_flow_to_flo(b200flow_ctx*, const double *uv, int B, int H, int W, unsigned char *out);
+
 /* ---- diagnostics (bench.py / ncu; no reference counterpart): CUDA-event time of `reps` solves of a synthetic batch of B
  *      random SPD five-point systems (coefficients spanning `decades` decades) run for exactly `iters` iterations */
 int b200flow_debug_pcg_bench(b200flow_ctx*, int B, int H, int W, int solver, int iters, int reps, double decades,

@@ -430,6 +430,64 @@ int b200flow_solve_increment_mc(b200flow_ctx *ctx, const b200flow_params *p, dou
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// evaluation / export edges
+// ------------------------------------------------------------------------------------------------
+int b200flow_flow_error_dev(b200flow_ctx *ctx, const double *uv_dev, const double *gt_dev, int B, int H, int W, int border,
+                            double *result /*host [B][4]*/) {
+  API_BEGIN(ctx);
+  if (!uv_dev || !gt_dev || !result || B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad arguments");
+  double *d_res;
+  BF_TRY(arena_alloc(ctx, &d_res, (size_t)4 * B));
+  BF_TRY(k_flow_error(ctx, (const double2 *)uv_dev, (const double2 *)gt_dev, B, H, W, border, d_res));
+  BF_TRY(download(ctx, result, d_res, (size_t)4 * B));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_flow_error(b200flow_ctx *ctx, const double *uv, const double *gt, int B, int H, int W, int border,
+                        double *result) {
+  API_BEGIN(ctx);
+  if (!uv || !gt || !result || B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad arguments");
+  size_t N = (size_t)B * H * W;
+  double *d_uv, *d_gt, *d_res;
+  BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
+  BF_TRY(upload(ctx, &d_gt, gt, 2 * N));
+  BF_TRY(arena_alloc(ctx, &d_res, (size_t)4 * B));
+  BF_TRY(k_flow_error(ctx, (const double2 *)d_uv, (const double2 *)d_gt, B, H, W, border, d_res));
+  BF_TRY(download(ctx, result, d_res, (size_t)4 * B));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_flow_to_color(b200flow_ctx *ctx, const double *uv, int B, int H, int W, double max_flow, unsigned char *rgb) {
+  API_BEGIN(ctx);
+  if (!uv || !rgb || B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad arguments");
+  size_t N = (size_t)B * H * W;
+  double *d_uv;
+  unsigned char *d_rgb;
+  BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
+  BF_TRY(arena_alloc(ctx, &d_rgb, 3 * N));
+  BF_TRY(k_flow_to_color(ctx, (const double2 *)d_uv, B, H, W, max_flow, d_rgb));
+  BF_TRY(download(ctx, rgb, d_rgb, 3 * N));
+  API_SYNC(ctx);
+  return 0;
+}
+
+int b200flow_flow_to_flo(b200flow_ctx *ctx, const double *uv, int B, int H, int W, unsigned char *out) {
+  API_BEGIN(ctx);
+  if (!uv || !out || B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad arguments");
+  size_t N = (size_t)B * H * W, bytes = (size_t)B * 12 + 8 * N;
+  double *d_uv;
+  unsigned char *d_out;
+  BF_TRY(upload(ctx, &d_uv, uv, 2 * N));
+  BF_TRY(arena_alloc(ctx, &d_out, bytes));
+  BF_TRY(k_flow_to_flo(ctx, (const double2 *)d_uv, B, H, W, d_out));
+  BF_TRY(download(ctx, out, d_out, bytes));
+  API_SYNC(ctx);
+  return 0;
+}
+
 // Diagnostic (bench / ncu only, not on the flow path): time `reps` solves of a synthetic batch of B five-point systems
 // of H x W pixels (random SPD coefficients spanning `decades` decades) run for exactly `iters` iterations each.
 __global__ void synth_system_kernel(bf::LinSys S, double decades, unsigned seed) {

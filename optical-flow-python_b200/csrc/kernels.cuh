@@ -95,6 +95,12 @@ int k_weighted_median(b200flow_ctx *, const double2 *cand, const double2 *base, 
                       const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out);
 int k_hs_norm_gate(b200flow_ctx *, const double2 *x, int B, long long n, int *active, double *scratch);
 
+// ---- eval.cu
+int k_flow_error(b200flow_ctx *, const double2 *uv, const double2 *gt, int B, int H, int W, int border,
+                 double *result /*[B][4] = AAE, std, AEPE, valid count*/);
+int k_flow_to_color(b200flow_ctx *, const double2 *uv, int B, int H, int W, double max_flow, unsigned char *rgb);
+int k_flow_to_flo(b200flow_ctx *, const double2 *uv, int B, int H, int W, unsigned char *out /*[B][12 + 8HW]*/);
+
 // ---- pipeline.cu
 int run_pipeline(b200flow_ctx *, const b200flow_params *p, int B, int H, int W, int NC, int C, const double *gray_planar,
                  const double *color_planar, const double2 *init, double2 *uv_out, b200flow_stats *stats);

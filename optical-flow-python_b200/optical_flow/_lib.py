@@ -79,6 +79,10 @@ _SIGS = {
     "b200flow_solve_increment_mc": [C.POINTER(Params), C.c_double, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                     _vp, _ip, _dp],
     "b200flow_detect_occlusion_mc": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp],
+    "b200flow_flow_error": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    "b200flow_flow_error_dev": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    "b200flow_flow_to_color": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp],
+    "b200flow_flow_to_flo": [_vp, C.c_int, C.c_int, C.c_int, _vp],
     "b200flow_debug_pcg_bench": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["b200flow_abi_version", "b200flow_ctx_create", "b200flow_ctx_destroy",

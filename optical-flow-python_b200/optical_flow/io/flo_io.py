@@ -30,6 +30,24 @@ def write_flo(flow, filename):
         f.write(np.ascontiguousarray(flow, dtype='<f4').tobytes())
 
 
+def flo_bytes(flow):
+    """The byte image of write_flo(flow, ...) built on the device (b200flow_flow_to_flo): (H, W, 2) -> bytes, or
+    (B, H, W, 2) -> list of bytes.  Lets a batch benchmarking loop export float32 .flo payloads without first bringing
+    the float64 fields to the host."""
+    from optical_flow import _lib
+    flow = _lib.f64(flow)
+    single = flow.ndim == 3
+    if single:
+        flow = flow[None]
+    if flow.ndim != 4 or flow.shape[3] != 2:
+        raise ValueError(f"Flow must be (H, W, 2) array, got shape {flow.shape}")
+    B, H, W = flow.shape[:3]
+    out = np.empty((B, 12 + 8 * H * W), dtype=np.uint8)
+    _lib.default_context().call("b200flow_flow_to_flo", _lib.ptr(flow), B, H, W, _lib.ptr(out))
+    res = [out[b].tobytes() for b in range(B)]
+    return res[0] if single else res
+
+
 def read_flow_file(seq_name, i_seq, data_dir=None):
     """(im1, im2, tu, tv) of a Middlebury sequence under data_dir/other-data and data_dir/other-gt-flow."""
     from PIL import Image

@@ -15,6 +15,7 @@ Files written (tests/golden/):
   e2e_<preset>.npz    estimate_flow() final uv on a 64x80 RubberWhale crop, every in-scope preset
   tape_<preset>.npz   teacher-forcing tape (uv at the start of selected warp iterations + outputs)
   multichannel.npz    two-channel frames: channel-mean data term, occlusion, ROF, end-to-end flows
+  eval.npz            flow_angular_error / flow_to_color / write_flo outputs of the reference
   sor.npz             legacy solver='sor' results (tiny windows: the reference's SOR is a per-row Python loop)
   rubberwhale_full.npz (--full) estimate_flow(RubberWhale, 'classic+nl-fast') final uv + AAE/AEPE
   rubberwhale_10_11.npz the two RGB frames + .flo ground truth as uint8 / float32 arrays (fixture data)
@@ -402,6 +403,32 @@ def gen_sor(im1, im2, stages):
     save("sor.npz", **res)
 
 
+def gen_eval(tu, tv):
+    """Evaluation / export edges: metrics, Middlebury colour coding, .flo bytes."""
+    import tempfile
+    from optical_flow.viz.flow_color import flow_to_color
+    from optical_flow.io.flo_io import write_flo
+    rng = np.random.default_rng(3)
+    sl = (slice(100, 196), slice(200, 330))
+    gt = np.stack([tu[sl], tv[sl]], axis=2).astype(float)          # contains unknown-flow pixels (1e10)
+    H, W = gt.shape[:2]
+    est = np.where(np.abs(gt) < 1e9, gt, 0.0) + 0.3 * smooth_flow(rng, H, W, 1.0) + 0.01 * rng.standard_normal((H, W, 2))
+    res = {"gt": gt, "est": est}
+    for border in (0, 5):
+        res["metrics_b%d" % border] = np.array(flow_angular_error(gt[:, :, 0], gt[:, :, 1], est[:, :, 0], est[:, :, 1], border))
+    big = est * 4.0
+    big[3:9, 4:20] = 1e10                                           # unknown pixels -> black
+    res["big"] = big
+    res["color_auto"] = flow_to_color(est)
+    res["color_max2"] = flow_to_color(big, max_flow=2.0)
+    res["color_auto_unknown"] = flow_to_color(big)
+    with tempfile.TemporaryDirectory() as d:
+        fn = os.path.join(d, "a.flo")
+        write_flo(est, fn)
+        res["flo_bytes"] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
+    save("eval.npz", **res)
+
+
 def gen_full(im1, im2, tu, tv):
     t0 = time.time()
     uv = quiet(estimate_flow, im1, im2, "classic+nl-fast")
@@ -430,6 +457,8 @@ def main():
         gen_tape(im1, im2, "ba", {"max_iters": 2}, "_mi2")
     if args.only in (None, "multichannel"):
         gen_multichannel(im1, im2)
+    if args.only in (None, "eval"):
+        gen_eval(tu, tv)
     if args.only in (None, "sor"):
         gen_sor(im1, im2, dict(np.load(os.path.join(HERE, "stages.npz"))))
     if args.full or args.only == "full":
