@@ -415,7 +415,8 @@ __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const doubl
 
 // algorithmic bytes per pixel, single-channel frames: read uv 16 + im1,I1x,I1y 24 + gathered source 32,
 // write D 16 + a12 8 + WH 16 + WV 16 + rhs 16  = 144 B   (NC channels: 88 + 56 NC)
-__global__ void __launch_bounds__(256) warp_assemble_kernel(const double *__restrict__ frames, long long bstride, int NC,
+template <bool MULTI>   // MULTI: NC > 1 (kept out of the single-channel instantiation: it doubles the register count)
+__global__ void __launch_bounds__(256, MULTI ? 1 : 3) warp_assemble_kernel(const double *__restrict__ frames, long long bstride, int NC,
                                      const double *__restrict__ I1x,
                                      const double *__restrict__ I1y, const double4 *__restrict__ src2,
                                      const double2 *__restrict__ uv, const double2 *__restrict__ duv, int H, int W,
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(256) warp_assemble_kernel(const double *__rest
   const double2 f = uv[off + i];
   const double2 dc = duv ? duv[off + i] : make_double2(0.0, 0.0);
   DataTerm dt;
-  if (NC == 1) {
+  if (!MULTI) {
     Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride, I1x + off, I1y + off, src2 + off, H, W, x, y, f,
                            interp, blend);
     if (It) { It[off + i] = dv.It; Ix[off + i] = dv.Ix; Iy[off + i] = dv.Iy; }
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(256) warp_assemble_kernel(const double *__rest
 }
 
 // It, Ix, Iy: [B][NC][H][W]
-__global__ void __launch_bounds__(256) assemble_from_deriv_kernel(const double *__restrict__ It, const double *__restrict__ Ix,
+__global__ void __launch_bounds__(256, 3) assemble_from_deriv_kernel(const double *__restrict__ It, const double *__restrict__ Ix,
                                            const double *__restrict__ Iy, int NC, const double2 *__restrict__ uv,
                                            const double2 *__restrict__ duv, int H, int W, PenaltySet ps, LinSys sys) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -484,8 +485,12 @@ int k_warp_assemble(b200flow_ctx *ctx, const double *frames, long long bstride, 
   if (interp < 0 || interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", interp);
   dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
   int do_assemble = sys.D != nullptr;
-  BF_LAUNCH(ctx, warp_assemble_kernel, grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp, blend, ps,
-            sys, It, Ix, Iy, do_assemble);
+  if (NC == 1)
+    BF_LAUNCH(ctx, warp_assemble_kernel<false>, grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp,
+              blend, ps, sys, It, Ix, Iy, do_assemble);
+  else
+    BF_LAUNCH(ctx, warp_assemble_kernel<true>, grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp,
+              blend, ps, sys, It, Ix, Iy, do_assemble);
   return 0;
 }
 
