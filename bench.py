@@ -319,9 +319,15 @@ def main():
         e2e_value = pairs / (ms_e2e / 1e3)
         # roofline of the solver kernel: per-rank algorithmic bytes / per-rank solver time
         achieved = (pixel_iters * PCG_BYTES_PER_PIXEL_ITER) / (solver_ms / 1e3) / 1e9 if solver_ms > 0 else 0.0
-        traffic = None
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, like `achieved`'s
+        # numerator); only quoted for the kernel it was captured on
+        traffic = traffic_detail = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "pcg_traffic.json"))).get("dram_bytes_per_pixel_iter")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "pcg_traffic.json")))
+            if tj.get("kernel") == ("pcg_mixed_kernel" if args.solver_precision == "mixed" else "pcg_kernel"):
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_detail = {k: tj.get(k) for k in ("capture", "algorithmic_bytes_this_launch",
+                                                         "dram_bytes_per_pixel_iter", "algorithmic_bytes_per_pixel_iter")}
         except (OSError, ValueError):
             pass
         line = {
@@ -344,7 +350,7 @@ def main():
             "roofline": {"kernel": "%s (persistent cooperative PCG, solve.cu)" %
                                    ("pcg_mixed_kernel" if args.solver_precision == "mixed" else "pcg_kernel"), "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": traffic,
+                         "peak_source": peak_src, "traffic": traffic, "traffic_detail": traffic_detail,
                          "bytes_per_pixel_iter": PCG_BYTES_PER_PIXEL_ITER, "pixel_iters_per_step": pixel_iters / args.steps,
                          "solver_ms_per_step": solver_ms / args.steps,
                          "solver_share_of_step": solver_ms / ms_resident if ms_resident else None},
