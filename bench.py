@@ -39,7 +39,9 @@ H, W = 480, 640
 # algorithmic bytes per pixel per PCG iteration (DESIGN.md section 4 / solve.cu headers):
 #   mixed (default): fp32 Krylov vectors + fp32 coefficient copy, phase A 76 B + phase B 44 B
 #   fp64           : every vector fp64, phase A 152 B + phase B 76 B
-PCG_BYTES = {"mixed": 120, "fp64": 228}
+PCG_BYTES = {"mixed": 128, "mixed-jacobi": 120, "fp64": 228}
+PCG_KERNEL = {"mixed": "pcg_ic_kernel", "mixed-jacobi": "pcg_mixed_kernel", "fp64": "pcg_kernel"}
+PCG_PRECOND = {"mixed": "tile-local block-IC(0)", "mixed-jacobi": "block-Jacobi", "fp64": "block-Jacobi"}
 SAMPLE_H, SAMPLE_W = 120, 160         # CPU-baseline sample: centre crop with 1/16 of the pixels
 
 
@@ -203,8 +205,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="frame pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--solver-precision", default="mixed", choices=["mixed", "fp64"],
-                    help="mixed: fp32 Krylov vectors with fp64 reliable updates (default); fp64: all-fp64 PCG (variant)")
+    ap.add_argument("--solver-precision", default="mixed", choices=["mixed", "mixed-jacobi", "fp64"],
+                    help="mixed: fp32 Krylov vectors with fp64 reliable updates, tile-local block-IC(0) preconditioner "
+                         "(default); mixed-jacobi: same with the block-Jacobi preconditioner; fp64: all-fp64 PCG (variants)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -324,7 +327,7 @@ def main():
         traffic = traffic_detail = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "pcg_traffic.json")))
-            if tj.get("kernel") == ("pcg_mixed_kernel" if args.solver_precision == "mixed" else "pcg_kernel"):
+            if tj.get("kernel") == PCG_KERNEL[args.solver_precision]:
                 traffic = tj.get("dram_bytes_per_launch")
                 traffic_detail = {k: tj.get(k) for k in ("capture", "algorithmic_bytes_this_launch",
                                                          "dram_bytes_per_pixel_iter", "algorithmic_bytes_per_pixel_iter")}
@@ -339,16 +342,18 @@ def main():
                                    "%d pairs per GPU per step" % B,
                        "method": METHOD, "height": H, "width": W, "pairs_per_gpu_per_step": B,
                        "parallelism": "independent frame pairs per GPU, no collective",
-                       "solver": "block-Jacobi PCG until the fp64 true residual ||b-Ax|| <= %g ||b|| (stands in for spsolve); %s"
-                                 % (P.tol, "Krylov vectors fp32, solution + residual replacement fp64" if
-                                    args.solver_precision == "mixed" else "all vectors fp64"),
+                       "solver": "%s PCG until the fp64 true residual ||b-Ax|| <= %g ||b|| (stands in for spsolve); %s"
+                                 % (PCG_PRECOND[args.solver_precision], P.tol,
+                                    "Krylov vectors fp32, solution + residual replacement fp64" if
+                                    args.solver_precision != "fp64" else "all vectors fp64"),
                        "solver_precision": args.solver_precision,
                        "l2": "per-step working set ~%.1f GB per GPU >> 126 MB L2; no flush needed" % (B * H * W * 450 / 1e9)},
             "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(2 * B * H * W * 3), "d2h_bytes_per_step": int(B * H * W * 2 * 8)},
             "gpu_launches": int(launches_all),
-            "roofline": {"kernel": "%s (persistent cooperative PCG, solve.cu)" %
-                                   ("pcg_mixed_kernel" if args.solver_precision == "mixed" else "pcg_kernel"), "bound": "hbm",
+            "roofline": {"kernel": "%s (persistent cooperative PCG, solve%s.cu)" %
+                                   (PCG_KERNEL[args.solver_precision], "_ic" if args.solver_precision == "mixed" else ""),
+                         "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic, "traffic_detail": traffic_detail,
                          "bytes_per_pixel_iter": PCG_BYTES_PER_PIXEL_ITER, "pixel_iters_per_step": pixel_iters / args.steps,

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200flow.so")
-SOURCES = ["pre.cu", "warp.cu", "solve.cu", "filter.cu", "eval.cu", "pipeline.cu", "api.cu"]
+SOURCES = ["pre.cu", "warp.cu", "solve.cu", "solve_ic.cu", "filter.cu", "eval.cu", "pipeline.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -28,11 +28,12 @@ struct LinSys {                // matrix-free 2N x 2N system, B systems of H x W
 
 struct PcgWork {               // scratch vectors + reduction buffers for the persistent PCG kernel
   double2 *r, *p, *p2, *z, *Ap; // residual, search direction (ping-pong), preconditioned residual, A p
-  float *Minv;                 // 3 planes: m11, m12, m22 (block-Jacobi inverse, fp32) [3][B*H*W]
+  float *Minv;                 // 3 planes: m11, m12, m22 (block-Jacobi inverse / IC pivot inverse, fp32) [3][B*H*W]
+  uint2 *wpk;                  // IC preconditioner: edge weights as truncated bf16 pairs {wuh,wvh},{wuv,wvv} [B*H*W]
   double *partial;             // [3][B][grid]
   double *scal;                // per-system scalars [8][B]
   int *flags;                  // [0]=ndone, [1..B]=done[b], then iters[b]
-  int grid, grid_mixed;        // resident grid sizes of pcg_kernel / pcg_mixed_kernel
+  int grid, grid_mixed, grid_ic;   // resident grid sizes of pcg_kernel / pcg_mixed_kernel / pcg_ic_kernel
 };
 
 // ---- pre.cu
@@ -73,8 +74,11 @@ int pcg_work_alloc(b200flow_ctx *, int B, int H, int W, PcgWork *w);
 enum { PCG_MODE_MIXED = 0,        // block-Jacobi PCG, fp32 Krylov vectors + fp64 reliable updates (B200FLOW_SOLVER_EXACT)
        PCG_MODE_JACOBI_F64 = 1,   // scalar-Jacobi all-fp64 PCG: the reference's own 'pcg' mode (B200FLOW_SOLVER_PCG)
        PCG_MODE_BLOCK_F64 = 2,    // block-Jacobi all-fp64 PCG (B200FLOW_SOLVER_EXACT_F64)
-       PCG_MODE_SOR = 3 };        // the reference's legacy lexicographic SOR, omega 1.9 (B200FLOW_SOLVER_SOR)
+       PCG_MODE_SOR = 3,          // the reference's legacy lexicographic SOR, omega 1.9 (B200FLOW_SOLVER_SOR)
+       PCG_MODE_MIXED_IC = 4 };   // as MIXED with the tile-local block-IC(0) preconditioner (B200FLOW_SOLVER_EXACT_IC)
 inline int pcg_mode_of(int solver) { return solver; }
+// algorithmic bytes per pixel-iteration of a solver mode (roofline accounting; solve.cu / solve_ic.cu headers)
+inline int pcg_bytes_per_pixel_iter(int mode) { return mode == PCG_MODE_MIXED_IC ? 128 : mode == PCG_MODE_MIXED ? 120 : 228; }
 int k_pcg_solve(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                 int *iters_host /*[B] or null*/, double *relres_host /*[B] or null*/, bool sync_results);
 int k_pcg_solve_async(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,

@@ -78,7 +78,7 @@ int check_params(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
   if (B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad batch/size B=%d H=%d W=%d", B, H, W);
   if (p->method < 0 || p->method > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown method %d", p->method);
   if (p->interp < 0 || p->interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", p->interp);
-  if (p->solver < B200FLOW_SOLVER_EXACT || p->solver > B200FLOW_SOLVER_SOR)
+  if (p->solver < B200FLOW_SOLVER_EXACT || p->solver > B200FLOW_SOLVER_EXACT_IC)
     return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
   if (!(p->pyramid_spacing > 1.0) || p->pyramid_spacing > 8.0)
     return set_err(ctx, B200FLOW_EINVAL, "pyramid_spacing %g out of range (1, 8]", p->pyramid_spacing);
@@ -252,7 +252,7 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
             for (int b = 0; b < B; ++b) { int v = fl[1 + B + b]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; }
             fprintf(stderr, "[b200flow trace] gnc %d level %d (%dx%d) warp %d: solve %.3f ms, iters min %d mean %.1f max %d, "
                             "%.1f us/iter(max), alg %.0f GB/s\n", ignc, l, h, w, it, ms, mn, (double)sum / B, mx,
-                    mx ? 1e3 * ms / mx : 0.0, ms > 0 ? (double)sum * hw * (pcg_mode == PCG_MODE_MIXED ? 120 : 228) / (ms * 1e6) : 0.0);
+                    mx ? 1e3 * ms / mx : 0.0, ms > 0 ? (double)sum * hw * pcg_bytes_per_pixel_iter(pcg_mode) / (ms * 1e6) : 0.0);
           }
           solves++;
           tm.begin(T_FILTER);

@@ -13,17 +13,11 @@
 // Dot products: per-thread accumulation -> warp shuffle tree -> shared -> one double per (CTA, system),
 // then every CTA re-reduces the per-CTA partials of the systems it owns in a fixed order, so all CTAs get
 // bit-identical scalars and results are run-to-run deterministic (no floating-point atomics).
-#include <cooperative_groups.h>
-#include "kernels.cuh"
+#include "solve_shared.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace bf {
-
-constexpr int PCG_THREADS = 256;
-constexpr int TILE_W = 32, TILE_H = 8;
-constexpr int MAXLOC = 32;       // systems one CTA may touch
-constexpr double PCG_RELIABLE_DELTA = 0.01;  // mixed precision: fp64 residual replacement when |r| fell 100x
 
 struct PcgParams {
   LinSys sys;
@@ -35,63 +29,6 @@ struct PcgParams {
   int tiles_x, tiles_y, tiles_per_sys, tiles_per_cta;
   long long total_tiles;
 };
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// block-wide sum of two accumulators; result valid in thread 0
-__device__ __forceinline__ void block_sum2(double &a, double &b, double (*sm)[PCG_THREADS / 32]) {
-  a = warp_sum(a);
-  b = warp_sum(b);
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();   // protect sm reuse
-  if (l == 0) { sm[0][w] = a; sm[1][w] = b; }
-  __syncthreads();
-  if (w == 0) {
-    a = l < PCG_THREADS / 32 ? sm[0][l] : 0.0;
-    b = l < PCG_THREADS / 32 ? sm[1][l] : 0.0;
-    a = warp_sum(a);
-    b = warp_sum(b);
-  }
-}
-
-// fixed-order reduction of the per-CTA partials of system b; executed by warp 0, result in all its lanes
-__device__ __forceinline__ double reduce_partials(const double *part, int G, int b, int c_lo, int c_hi) {
-  const volatile double *q = part + (long long)b * G;
-  double s = 0.0;
-  for (int c = c_lo + (threadIdx.x & 31); c <= c_hi; c += 32) s += q[c];
-  return warp_sum(s);
-}
-
-struct Stencil {
-  double2 d; double a12; double2 wr, wl, wd, wu;   // own right/down edges, left/up neighbours' edges
-};
-
-__device__ __forceinline__ Stencil load_stencil(const LinSys &S, long long i, int x, int y) {
-  Stencil s;
-  s.d = __ldg(&S.D[i]);
-  s.a12 = __ldg(&S.a12[i]);
-  s.wr = __ldg(&S.WH[i]);
-  s.wd = __ldg(&S.WV[i]);
-  s.wl = x > 0 ? __ldg(&S.WH[i - 1]) : make_double2(0.0, 0.0);
-  s.wu = y > 0 ? __ldg(&S.WV[i - S.W]) : make_double2(0.0, 0.0);
-  return s;
-}
-
-__device__ __forceinline__ double2 apply_stencil(const Stencil &s, const double2 *v, long long i, int x, int y, int H,
-                                                 int W) {
-  double2 c = v[i];
-  double au = s.d.x * c.x + s.a12 * c.y;
-  double av = s.a12 * c.x + s.d.y * c.y;
-  if (x + 1 < W) { double2 n = v[i + 1]; au += s.wr.x * (c.x - n.x); av += s.wr.y * (c.y - n.y); }
-  if (x > 0)     { double2 n = v[i - 1]; au += s.wl.x * (c.x - n.x); av += s.wl.y * (c.y - n.y); }
-  if (y + 1 < H) { double2 n = v[i + W]; au += s.wd.x * (c.x - n.x); av += s.wd.y * (c.y - n.y); }
-  if (y > 0)     { double2 n = v[i - W]; au += s.wu.x * (c.x - n.x); av += s.wu.y * (c.y - n.y); }
-  return make_double2(au, av);
-}
 
 // p_new = z + beta * p_old at pixel j (computed on the fly: phase C of the textbook algorithm is fused into the matvec)
 __device__ __forceinline__ double2 pnew_at(const double2 *z, const double2 *pold, long long j, double beta) {
@@ -368,24 +305,6 @@ __global__ void __launch_bounds__(PCG_THREADS, PCG_MINB) pcg_kernel(PcgParams P)
 // are still ACTIVE be re-dealt over the whole grid each time a system finishes, so a batch whose systems need different
 // iteration counts keeps every SM streaming until the last one is done.
 // ------------------------------------------------------------------------------------------------
-constexpr int MAXB = 128;        // systems per mixed-precision solve (one scalar-update thread per system)
-
-struct MixWork {
-  float2 *r, *z, *p, *p2, *Ap, *y;
-  float2 *D, *WH, *WV;
-  float *a12;
-};
-
-struct MixParams {
-  LinSys sys;
-  PcgWork w;
-  MixWork m;
-  double2 *x;
-  double tol2, delta2;
-  int maxit;
-  int tiles_x, tiles_y, tiles_per_sys;
-};
-
 // cold paths of the mixed kernel (initialisation, reliable update)
 __device__ __forceinline__ double2 mix_init_pixel(const MixParams &P, long long i, int px, int py, long long n_all,
                                                float2 *pold) {
@@ -885,7 +804,7 @@ __global__ void pcg_stats_kernel(const int *flags, int B, long long hw, long lon
 
 size_t pcg_work_bytes(const b200flow_ctx *ctx, int B, int H, int W) {
   size_t n = (size_t)B * H * W;
-  return n * (5 * sizeof(double2) + 3 * sizeof(float)) + 4 * (size_t)B * ctx->num_sms * 8 * 8 + 64 * B + 4096;
+  return n * (5 * sizeof(double2) + 3 * sizeof(float) + sizeof(uint2)) + 4 * (size_t)B * ctx->num_sms * 8 * 8 + 64 * B + 4096;
 }
 
 static int pcg_grid(b200flow_ctx *ctx, int *grid_out, int *grid_mixed_out) {
@@ -910,13 +829,16 @@ int pcg_work_alloc(b200flow_ctx *ctx, int B, int H, int W, PcgWork *w) {
   BF_TRY(pcg_grid(ctx, &G, &Gm));
   w->grid = G;
   w->grid_mixed = Gm;
+  BF_TRY(pcg_ic_grid(ctx, &w->grid_ic));
   if (Gm > G) G = Gm;
+  if (w->grid_ic > G) G = w->grid_ic;
   BF_TRY(arena_alloc(ctx, &w->r, n));
   BF_TRY(arena_alloc(ctx, &w->p, n));
   BF_TRY(arena_alloc(ctx, &w->p2, n));
   BF_TRY(arena_alloc(ctx, &w->z, n));
   BF_TRY(arena_alloc(ctx, &w->Ap, n));
   BF_TRY(arena_alloc(ctx, &w->Minv, 3 * n));
+  BF_TRY(arena_alloc(ctx, &w->wpk, n));
   BF_TRY(arena_alloc(ctx, &w->partial, (size_t)4 * B * G));   // G = the larger of the two kernels' grids
   BF_TRY(arena_alloc(ctx, &w->scal, (size_t)B));
   BF_TRY(arena_alloc(ctx, &w->flags, (size_t)(1 + 2 * B)));
@@ -925,7 +847,7 @@ int pcg_work_alloc(b200flow_ctx *ctx, int B, int H, int W, PcgWork *w) {
 
 int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                 int *iters_host, double *relres_host, bool sync_results) {
-  const bool mixed = mode == PCG_MODE_MIXED;
+  const bool mixed = mode == PCG_MODE_MIXED || mode == PCG_MODE_MIXED_IC;
   const int tiles_x = (int)cdiv(sys.W, TILE_W), tiles_y = (int)cdiv(sys.H, TILE_H);
   const int tiles_per_sys = tiles_x * tiles_y;
   const long long total_tiles = (long long)tiles_per_sys * sys.B;
@@ -947,6 +869,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     P.delta2 = PCG_RELIABLE_DELTA * PCG_RELIABLE_DELTA;
     P.maxit = maxit;
     P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.tiles_per_sys = tiles_per_sys;
+    P.debug = 0;
     P.w.grid = G;
     // the fp32 working set (76 B / pixel) is carved out of the five fp64 vectors (80 B / pixel) of the work area
     const size_t n = (size_t)sys.B * sys.H * sys.W;
@@ -955,8 +878,19 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     P.m.Ap = reinterpret_cast<float2 *>(w.p2); P.m.y = P.m.Ap + n;
     P.m.D = reinterpret_cast<float2 *>(w.z);   P.m.WH = P.m.D + n;
     P.m.WV = reinterpret_cast<float2 *>(w.Ap); P.m.a12 = reinterpret_cast<float *>(P.m.WV + n);
-    void *args[] = {&P};
-    BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_mixed_kernel, dim3(G), dim3(PCG_THREADS), args, 0, ctx->stream));
+    if (mode == PCG_MODE_MIXED_IC) {
+      BF_TRY(k_pcg_ic_launch(ctx, P, w.grid_ic));
+    } else {
+      void *args[] = {&P};
+      const char *dbg = getenv("B200FLOW_MIX_SMEM");          // tuning experiment: shrink L1 like the IC kernel's carve-out does
+      const int dyn = dbg ? atoi(dbg) : 0;
+      if (dyn > 0) {
+        cudaFuncSetAttribute(pcg_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        const char *cv = getenv("B200FLOW_MIX_CARVEOUT");
+        cudaFuncSetAttribute(pcg_mixed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
+      }
+      BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_mixed_kernel, dim3(G), dim3(PCG_THREADS), args, dyn, ctx->stream));
+    }
   } else {
     PcgParams P;
     P.sys = sys; P.w = w; P.x = x;

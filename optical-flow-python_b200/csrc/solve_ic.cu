@@ -1,0 +1,787 @@
+// solve_ic.cu -- kernel group (4), default "exact" solver: mixed-precision PCG with reliable updates (as
+// pcg_mixed_kernel in solve.cu) preconditioned by a TILE-LOCAL 2x2-BLOCK INCOMPLETE CHOLESKY IC(0) instead of block
+// Jacobi.  Replaces scipy.sparse.linalg.spsolve behind BaseOpticalFlow._solve_linear_system (base.py:87-114).
+//
+// Why: the solver is HBM-bound (solve.cu), so the only way to make a solve much faster is FEWER iterations, and the
+// preconditioner may spend any amount of on-chip work as long as it adds little HBM traffic.  IC(0) of the five-point
+// block stencil needs no fill-in storage: M = (P + L) P^-1 (P + L)^T with L the strictly lower part of A itself and
+// P_i = A_ii - sum_{j in {left, up}} W_ij P_j^-1 W_ij (W_ij = diag(w_u, w_v) of the edge), so the preconditioner is
+// the 12 B/pixel P^-1 that block Jacobi already stores plus the edge weights the matvec reads anyway.  Couplings are
+// cut at the borders of 8-row x 32-column sub-tiles, which makes the two triangular solves local: a macro-tile of
+// 64 x 32 pixels (eight sub-tiles) is staged in shared memory and two warps sweep the eight sub-tiles along their
+// anti-diagonals (lane = row, 39 steps forward + 39 back, neighbours through warp shuffles, PUSH form so that both
+// sweeps use only the pixel's own coefficients).  scripts/ic_proto.py / ic32_proto.py (real Classic+NL systems):
+// 470 -> 211 iterations (alpha = 0), 60 -> 26 (alpha = 1), in fp32 exactly as done here.
+//
+// Algorithmic bytes per pixel-iteration (fp32 working set):
+//   A  read z 8, p_old 8, y 8, D 8, a12 4, WH 8, WV 8; write p 8, y 8, Ap 8                              = 76
+//   B  read r 8, Ap 8, P^-1 12, edges as 4 truncated bf16 8; write r 8, z 8                               = 52
+//                                                                                            total        128 B
+// Everything else (all-system scalar tracking, re-dealing of the active tiles, reliable updates on the fp64 true
+// residual, determinism) is as in pcg_mixed_kernel.
+#include "solve_shared.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace bf {
+
+#ifndef IC_THREADS
+#define IC_THREADS 256                         // threads per CTA: 256 (2 CTAs / SM) or 128 (4 CTAs / SM)
+#endif
+constexpr int IC_TH = IC_THREADS / 32;         // rows of one 32 x IC_TH thread tile (phase A: one pixel per thread)
+constexpr int IC_MW = 32, IC_MH = IC_TH * 8;   // macro-tile (pixels) staged in shared memory: every thread owns 8 rows x 1 column
+constexpr int IC_NPIX = IC_MW * IC_MH;
+// Footprint of a macro-tile in the IMAGE: its IC_THREADS / 32 strips of 8 rows x 32 columns (one per warp in phase B)
+// are laid out IC_GX across, so that a macro-tile row is IC_GX * 256 contiguous bytes of every float2 stream (whole
+// DRAM pages) instead of eight 256-byte pieces of eight different rows.  IC_GX = 1 is the vertical 64 x 32 stack.
+#ifndef IC_GX
+#define IC_GX 4
+#endif
+constexpr int IC_NSTRIP = IC_THREADS / 32;
+constexpr int IC_GY = IC_NSTRIP / IC_GX;
+constexpr int IC_MWPX = 32 * IC_GX, IC_MHPX = 8 * IC_GY;
+static_assert(IC_GX * IC_GY == IC_NSTRIP, "strips must tile the macro-tile");
+constexpr int IC_SUBH = 8;                     // sub-tile height (rows coupled by the incomplete factor)
+#ifndef IC_SW
+#define IC_SW 8                                // sub-tile width: 8, 16 or 32 (scripts/ic32_proto.py: 231 / 212 / 211 iterations)
+#endif
+static_assert(IC_GX == 1 || IC_SW == 8, "the horizontal layout needs warp-independent 8 x 8 sub-tiles");
+constexpr int IC_STEPS = IC_SW + IC_SUBH - 1;  // anti-diagonals of one sub-tile
+constexpr int IC_SWEEP_WARPS = IC_MH / IC_SW;  // lanes needed = IC_MH rows x (32 / IC_SW) column blocks
+constexpr int IC_SUBS = IC_MH / IC_TH;         // 32 x IC_TH thread tiles per macro-tile (= 8)
+// staged per pixel: float4 {i11, i12, i22, bf16x2 {wuh, wvh}} + bf16x2 {wuv, wvv} + float2 r = 28 B
+constexpr size_t IC_SMEM = (size_t)IC_NPIX * (sizeof(float4) + sizeof(unsigned) + sizeof(float2));   // 56 KB
+
+// shared-memory slot of macro-tile pixel (row, col): every row is rotated by
+//   sigma(row) = 2 (row mod 8) + 8 ((row / 8) mod (IC_SW / 8))
+// so that both access patterns are bank-conflict free for 4-, 8- and 16-byte elements: a warp touching one row
+// (lane = column), and a warp walking the anti-diagonals of its four sub-tiles (lane = (sub-tile q, row j), column =
+// column block + step - j): the physical column is then (step + lane + const) mod 32.
+__device__ __forceinline__ int ic_sigma(int row) { return 2 * (row & 7) + 8 * ((row >> 3) & (IC_SW / 8 - 1)); }
+__device__ __forceinline__ int ic_slot(int row, int col) { return row * IC_MW + ((col + ic_sigma(row)) & 31); }
+
+// edge weights are kept as truncated bfloat16 pairs in the preconditioner (never in the operator): rounding TOWARDS
+// ZERO keeps the perturbed matrix a diagonally dominant M-matrix, so the incomplete factorisation still exists, and the
+// factor is computed from the same truncated values, so M stays symmetric positive definite.  Iteration counts are
+// unchanged (scripts/ic32_proto.py: 211 vs 211).
+__device__ __forceinline__ unsigned ic_pack(float lo, float hi) {
+  return (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
+}
+__device__ __forceinline__ float ic_lo(unsigned p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float ic_hi(unsigned p) { return __uint_as_float(p & 0xffff0000u); }
+
+// ---- shared-memory access by 32-bit shared-space address (computed once per kernel): keeps the generic-to-shared
+//      window arithmetic (an S2R of the cluster CTA id per access) out of the latency-bound wavefront loops
+__device__ __forceinline__ float4 lds128(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned lds32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(unsigned a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts32(unsigned a, unsigned v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// block-wide sum of two accumulators over IC_THREADS threads; result valid in thread 0
+__device__ __forceinline__ void ic_block_sum2(double &a, double &b, double (*sm)[IC_THREADS / 32]) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();   // protect sm reuse
+  if (l == 0) { sm[0][w] = a; sm[1][w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    a = l < IC_THREADS / 32 ? sm[0][l] : 0.0;
+    b = l < IC_THREADS / 32 ? sm[1][l] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+}
+
+// With 8 x 8 sub-tiles the four sub-tiles a warp sweeps are exactly the 8 x 32 strip the same warp stages (thread
+// (ty, tx) owns rows 8 ty .. 8 ty + 7 of column tx), so the warps of a CTA never exchange data in phase B: a warp
+// barrier replaces the two block barriers and the 16 warps of an SM drift apart, overlapping one warp's global loads
+// with another's sweep.
+__device__ __forceinline__ void ic_stage_sync() {
+  if (IC_SW == 8) __syncwarp(); else __syncthreads();
+}
+
+// global loads of phase B as volatile asm: the compiler otherwise sinks each load down to its first use to save
+// registers (the kernel sits at the 128-register cap), which turned one batch of 24 loads per half-tile into seven
+// dependent round trips to DRAM (ncu: seven long-scoreboard stall points per tile).  Volatile asm statements keep their
+// program order, so the whole batch is in flight before the first value is consumed.
+__device__ __forceinline__ float2 ldg_f2(const float2 *p) {
+  float2 v;
+  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_nc_f(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg_nc_u2(const uint2 *p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+struct IcSmem {            // shared-space byte addresses of the three staged arrays
+  unsigned c0, cw, r;      // float4 {i11, i12, i22, bf16x2 wh}, bf16x2 wv, float2 r -> t -> z
+};
+
+// which sub-tile row this lane sweeps: warp w, lane (q = lane / 8, j = lane % 8) -> macro-tile row and first column
+struct IcLane { int row, col0; };
+__device__ __forceinline__ IcLane ic_lane(int w, int lane) {
+  const int q = lane >> 3, j = lane & 7;
+  int rb, cb;
+  if (IC_SW == 32) { rb = 4 * w + q; cb = 0; }
+  else if (IC_SW == 16) { rb = 2 * w + (q & 1); cb = q >> 1; }
+  else { rb = w; cb = q; }
+  IcLane L;
+  L.row = 8 * rb + j;
+  L.col0 = cb * IC_SW;
+  return L;
+}
+
+// ---- wavefront sweeps; executed by warps 0 .. IC_SWEEP_WARPS-1 ------------------------------------------------------
+// forward (P + L) t = r, backward (I + P^-1 L^T) z = t; r -> t -> z in place.  The down-edge weights {wuv, wvv} of
+// every sub-tile's LAST row are staged as 0, which cuts the coupling between sub-tiles without a select in the
+// dependent chain; the neighbour row is read with a rotating shuffle (lane 0 <- lane 31 is such a last row).  The
+// recurrences are arranged so that only two dependent FMAs follow each shuffle: everything that does not depend on
+// the shuffled value (products of coefficients, the own-row carry) is formed while the shuffle is in flight.
+__device__ __forceinline__ void ic_sweeps(const IcSmem sm, int w, int lane) {
+  const unsigned full = 0xffffffffu;
+  const IcLane L = ic_lane(w, lane);
+  const int j = lane & 7;
+  const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+  const int rb = L.row * IC_MW;
+  const int x0 = L.col0 + ic_sigma(L.row);               // physical column of logical column c: (x0 + c) & 31
+  {
+    float cu = 0.f, cv = 0.f, pu = 0.f, pv = 0.f;      // pushed from the left (own row) / pushed down to the next row
+    int c = -j;
+    int idx = rb + ((x0 + c) & 31);
+    float2 R = lds64(sm.r + idx * 8);
+    float4 A = lds128(sm.c0 + idx * 16);
+    unsigned Wv = lds32(sm.cw + idx * 4);
+#pragma unroll 1
+    for (int s = 0; s < IC_STEPS; ++s) {
+      const int idn = rb + ((x0 + c + 1) & 31);          // prefetch the next column (address independent of the chain)
+      const float2 Rn = lds64(sm.r + idn * 8);
+      const float4 An = lds128(sm.c0 + idn * 16);
+      const unsigned Wvn = lds32(sm.cw + idn * 4);
+      const float uu = __shfl_sync(full, pu, up_lane), uw = __shfl_sync(full, pv, up_lane);
+      const bool act = (unsigned)c < (unsigned)IC_SW;
+      const unsigned m = act ? 0xffffffffu : 0u;         // idle step (column outside the sub-tile): pushes nothing
+      const unsigned wh = __float_as_uint(A.w) & m, wv = Wv & m;
+      const float whu = ic_lo(wh), whv = ic_hi(wh), wvu = ic_lo(wv), wvv = ic_hi(wv);
+      const float bu = R.x + cu, bv = R.y + cv;
+      const float su = fmaf(A.x, bu, A.y * bv), sv = fmaf(A.y, bu, A.z * bv);     // t without the row above
+      const float kuu = wvu * A.x, kuw = wvu * A.y, kvu = wvv * A.y, kvw = wvv * A.z;
+      pu = fmaf(kuu, uu, fmaf(kuw, uw, wvu * su));       // = wuv * t_u   (critical chain: shuffle -> 2 FMA -> shuffle)
+      pv = fmaf(kvu, uu, fmaf(kvw, uw, wvv * sv));       // = wvv * t_v
+      const float tu = fmaf(A.x, uu, fmaf(A.y, uw, su)), tv = fmaf(A.y, uu, fmaf(A.z, uw, sv));
+      cu = whu * tu; cv = whv * tv;
+      if (act) sts64(sm.r + idx * 8, make_float2(tu, tv));
+      R = Rn; A = An; Wv = Wvn; idx = idn; ++c;
+    }
+  }
+  {
+    float zu = 0.f, zv = 0.f;                            // own z of the previous step = right neighbour, offered to the row above
+    int c = IC_STEPS - 1 - j;
+    int idx = rb + ((x0 + c) & 31);
+    float2 Tr = lds64(sm.r + idx * 8);
+    float4 A = lds128(sm.c0 + idx * 16);
+    unsigned Wv = lds32(sm.cw + idx * 4);
+#pragma unroll 1
+    for (int s = IC_STEPS - 1; s >= 0; --s) {
+      const int idn = rb + ((x0 + c - 1) & 31);
+      const float2 Tn = lds64(sm.r + idn * 8);
+      const float4 An = lds128(sm.c0 + idn * 16);
+      const unsigned Wvn = lds32(sm.cw + idn * 4);
+      const float du = __shfl_sync(full, zu, dn_lane), dv = __shfl_sync(full, zv, dn_lane);
+      const bool act = (unsigned)c < (unsigned)IC_SW;
+      const unsigned m = act ? 0xffffffffu : 0u;         // idle step: z = 0
+      const unsigned wh = __float_as_uint(A.w) & m, wv = Wv & m;
+      const float whu = ic_lo(wh), whv = ic_hi(wh), wvu = ic_lo(wv), wvv = ic_hi(wv);
+      const float2 T = make_float2(__uint_as_float(__float_as_uint(Tr.x) & m), __uint_as_float(__float_as_uint(Tr.y) & m));
+      // z = T + P^-1 (WH z_right + WV z_down), z_right = own previous z
+      const float bu = fmaf(A.x * whu, zu, fmaf(A.y * whv, zv, T.x));
+      const float bv = fmaf(A.y * whu, zu, fmaf(A.z * whv, zv, T.y));
+      const float kuu = A.x * wvu, kuw = A.y * wvv, kvu = A.y * wvu, kvw = A.z * wvv;
+      zu = fmaf(kuu, du, fmaf(kuw, dv, bu));
+      zv = fmaf(kvu, du, fmaf(kvw, dv, bv));
+      if (act) sts64(sm.r + idx * 8, make_float2(zu, zv));
+      Tr = Tn; A = An; Wv = Wvn; idx = idn; --c;
+    }
+  }
+}
+
+// incomplete factorisation of the staged macro-tile: c0 holds {a11 + sum w_u, a12, a22 + sum w_v, wh} on entry and the
+// inverted pivot blocks {i11, i12, i22, wh} on exit.  Same wavefront as the sweeps (three pushed values per direction).
+__device__ __forceinline__ void ic_factor(const IcSmem sm, int w, int lane) {
+  const unsigned full = 0xffffffffu;
+  const IcLane L = ic_lane(w, lane);
+  const int j = lane & 7;
+  const int up_lane = (lane + 31) & 31;
+  const int rb = L.row * IC_MW;
+  const int x0 = L.col0 + ic_sigma(L.row);
+  float c11 = 0.f, c12 = 0.f, c22 = 0.f, p11 = 0.f, p12 = 0.f, p22 = 0.f;
+  int c = -j;
+#pragma unroll 1
+  for (int s = 0; s < IC_STEPS; ++s, ++c) {
+    const bool act = (unsigned)c < (unsigned)IC_SW;
+    const int idx = rb + ((x0 + c) & 31);
+    const float4 A = lds128(sm.c0 + idx * 16);
+    const unsigned wh = __float_as_uint(A.w), wv = lds32(sm.cw + idx * 4);
+    const float whu = ic_lo(wh), whv = ic_hi(wh), wvu = ic_lo(wv), wvv = ic_hi(wv);
+    const float u11 = __shfl_sync(full, p11, up_lane), u12 = __shfl_sync(full, p12, up_lane),
+                u22 = __shfl_sync(full, p22, up_lane);           // 0 from a sub-tile's last row (its wuv, wvv are staged as 0)
+    double d11 = (double)A.x - ((double)c11 + (double)u11);
+    double d12 = (double)A.y - ((double)c12 + (double)u12);
+    double d22 = (double)A.z - ((double)c22 + (double)u22);
+    double det = d11 * d22 - d12 * d12;
+    if (!(d11 > 0.0 && d22 > 0.0 && det > 1e-10 * d11 * d22)) {      // pivot breakdown: keep the unmodified block
+      d11 = (double)A.x; d12 = (double)A.y; d22 = (double)A.z;
+      det = d11 * d22 - d12 * d12;
+    }
+    float i11, i12, i22;
+    if (d11 > 0.0 && d22 > 0.0 && det > 1e-14 * d11 * d22) {
+      const double inv = 1.0 / det;
+      i11 = (float)(d22 * inv); i12 = (float)(-d12 * inv); i22 = (float)(d11 * inv);
+    } else {                                                           // as block Jacobi's scalar fallback (solve.cu)
+      i11 = d11 > 1e-12 ? (float)(1.0 / d11) : 0.f;
+      i22 = d22 > 1e-12 ? (float)(1.0 / d22) : 0.f;
+      i12 = 0.f;
+    }
+    if (act) {
+      sts128(sm.c0 + idx * 16, make_float4(i11, i12, i22, A.w));
+      c11 = whu * whu * i11; c12 = whu * whv * i12; c22 = whv * whv * i22;
+      p11 = wvu * wvu * i11; p12 = wvu * wvv * i12; p22 = wvv * wvv * i22;
+    } else {
+      c11 = 0.f; c12 = 0.f; c22 = 0.f; p11 = 0.f; p12 = 0.f; p22 = 0.f;
+    }
+  }
+}
+
+// true residual at pixel i of the solution x + y + alpha p, fp64, evaluated on the fly at the five stencil points
+__device__ __forceinline__ double2 ic_true_residual(const MixParams &P, long long i, int px, int py, const float2 *pnew,
+                                                    double alpha) {
+  const LinSys &S = P.sys;
+  const int W = S.W, H = S.H;
+  const double2 *x = P.x;
+  const float2 *y = P.m.y;
+  const long long jl = px > 0 ? i - 1 : i, jr = px + 1 < W ? i + 1 : i;
+  const long long ju = py > 0 ? i - W : i, jd = py + 1 < H ? i + W : i;
+#define XTRUE(j, out)                                                           \
+  {                                                                             \
+    double2 xx = x[j]; float2 yy = y[j], pp = pnew[j];                          \
+    out = make_double2(xx.x + ((double)yy.x + alpha * (double)pp.x),            \
+                       xx.y + ((double)yy.y + alpha * (double)pp.y));           \
+  }
+  double2 c, nl, nr, nu, nd;
+  XTRUE(i, c) XTRUE(jl, nl) XTRUE(jr, nr) XTRUE(ju, nu) XTRUE(jd, nd)
+#undef XTRUE
+  const double2 sd = __ldg(&S.D[i]), swr = __ldg(&S.WH[i]), swd = __ldg(&S.WV[i]);
+  const double2 swl = __ldg(&S.WH[jl]), swu = __ldg(&S.WV[ju]);   // multiplied by a zero difference when jl == i / ju == i
+  const double sa12 = __ldg(&S.a12[i]);
+  double au = sd.x * c.x + sa12 * c.y;
+  double av = sa12 * c.x + sd.y * c.y;
+  au += swr.x * (c.x - nr.x); av += swr.y * (c.y - nr.y);
+  au += swl.x * (c.x - nl.x); av += swl.y * (c.y - nl.y);
+  au += swd.x * (c.x - nd.x); av += swd.y * (c.y - nd.y);
+  au += swu.x * (c.x - nu.x); av += swu.y * (c.y - nu.y);
+  const double2 rb = __ldg(&S.rhs[i]);
+  return make_double2(rb.x - au, rb.y - av);
+}
+
+#ifndef IC_UA
+#define IC_UA 2
+#endif
+
+__global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(MixParams P) {
+  cg::grid_group grid = cg::this_grid();
+  const LinSys &S = P.sys;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int H = S.H, W = S.W, B = S.B;
+  const long long HW = (long long)H * W;
+  const long long n_all = (long long)B * HW;
+  const int tps = P.tiles_per_sys;          // MACRO-tiles per system
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  int GW = 32;
+  while (GW > 1 && B * GW > IC_THREADS) GW >>= 1;
+
+  extern __shared__ __align__(16) unsigned char ic_smem[];
+  IcSmem sm;
+  sm.c0 = (unsigned)__cvta_generic_to_shared(ic_smem);             // float4 {i11, i12, i22, bf16x2 {wuh, wvh}}
+  asm volatile("mov.u32 %0, %0;" : "+r"(sm.c0));                   // opaque: must live in a register, never rematerialised
+  sm.r = sm.c0 + IC_NPIX * 16;                                     // float2 r -> t -> z
+  sm.cw = sm.r + IC_NPIX * 8;                                      // bf16x2 {wuv, wvv}
+
+  __shared__ double sm_red[2][IC_THREADS / 32];
+  __shared__ double s_rz[MAXB], s_bb[MAXB], s_alpha[MAXB], s_beta[MAXB], s_maxr2[MAXB], s_rzprev[MAXB];
+  __shared__ double s_ta[MAXB], s_tb[MAXB];
+  __shared__ int s_state[MAXB];          // 0 active, 1 finished, 2 converged: final flush pending, 3 reliable update in progress
+  __shared__ int s_bad[MAXB], s_flush[MAXB];
+  __shared__ int s_act[MAXB], s_pos[MAXB];   // compact list of unfinished systems and its inverse
+  __shared__ int s_nact, s_tpc;
+
+  double *part_a = P.w.partial;                         // [B][G]  p.Ap
+  double *part_b = P.w.partial + (long long)B * G;      // [B][G]  r.z
+  double *part_c = P.w.partial + 2LL * B * G;           // [B][G]  r.r
+  float *Minv = P.w.Minv;                               // [3][n_all] inverted IC pivot blocks
+  float2 *r = P.m.r, *z = P.m.z, *Ap = P.m.Ap, *y = P.m.y;
+  float2 *pold = P.m.p, *pnew = P.m.p2;
+  float2 *Df = P.m.D, *WHf = P.m.WH, *WVf = P.m.WV;
+  float *a12f = P.m.a12;
+  uint2 *Wpk = P.w.wpk;                                 // bf16 pairs {wuh, wvh}, {wuv, wvv}: the preconditioner's copy of the edges
+  double2 *x = P.x;
+  int *done_g = P.w.flags + 1;
+  int *iters_g = P.w.flags + 1 + B;
+  double *relres_g = P.w.scal;
+
+  // ---- macro-tile ownership: the macro-tiles of the unfinished systems, in compact order, are dealt to the CTAs in
+  //      contiguous chunks of s_tpc; recomputed (identically by every CTA) whenever a system finishes
+#define REMAP()                                                                         \
+  {                                                                                     \
+    __syncthreads();                                                                    \
+    if (tid == 0) {                                                                     \
+      int n = 0;                                                                        \
+      for (int b = 0; b < B; ++b) {                                                     \
+        if (s_state[b] != 1) { s_act[n] = b; s_pos[b] = n; ++n; } else s_pos[b] = -1;   \
+      }                                                                                 \
+      s_nact = n;                                                                       \
+      long long tt = (long long)n * tps;                                                \
+      s_tpc = tt > 0 ? (int)((tt + G - 1) / G) : 1;                                     \
+    }                                                                                   \
+    __syncthreads();                                                                    \
+  }
+#define C_LO(b) ((int)(((long long)s_pos[b] * tps) / s_tpc))
+#define C_HI(b) ((int)((((long long)(s_pos[b] + 1)) * tps - 1) / s_tpc))
+#define OWN_RANGE()                                                                              \
+  const long long t0 = (long long)cta * s_tpc;                                                   \
+  const long long tt_ = (long long)s_nact * tps;                                                 \
+  const long long t1 = t0 + s_tpc < tt_ ? t0 + s_tpc : tt_;                                      \
+  const int a_first = t0 < t1 ? (int)(t0 / tps) : 0;                                             \
+  const int a_last = t0 < t1 ? (int)((t1 - 1) / tps) : -1;
+#define TILE_RANGE(aslot)                                                                        \
+  const int b = s_act[aslot];                                                                    \
+  const long long tbase = (long long)(aslot) * tps;                                              \
+  const long long ta = tbase > t0 ? tbase : t0;                                                  \
+  const long long tb = tbase + tps < t1 ? tbase + tps : t1;                                      \
+  const long long base = (long long)b * HW;
+  // pixel of this thread in 32 x 8 thread tile v (v = macro-tile * 8 + sub-row-block) of the current system
+#define PIXEL_OF(v, px, py, i, ok)                                                               \
+  {                                                                                              \
+    int tl = (int)(((v) >> 3) - tbase);                                                          \
+    const int k_ = (int)((v) & 7) * IC_TH, st_ = k_ >> 3;        /* strip and row offset of sub-tile */ \
+    px = (tl % P.tiles_x) * IC_MWPX + (st_ % IC_GX) * 32 + tx;                                   \
+    py = (tl / P.tiles_x) * IC_MHPX + (st_ / IC_GX) * 8 + (k_ & 7) + ty;                         \
+    ok = (v) < tb * IC_SUBS && px < W && py < H;                                                 \
+    i = ok ? base + (long long)py * W + px : base;                                               \
+  }
+#define REDUCE_ALL(pa, pb, want)                                                        \
+  {                                                                                     \
+    const int b = tid / GW, gl = tid % GW;                                              \
+    double va = 0.0, vb = 0.0;                                                          \
+    if (b < B && s_state[b] == (want)) {                                                \
+      const int c_lo = C_LO(b), c_hi = C_HI(b);                                         \
+      const volatile double *qa = (pa) + (long long)b * G;                              \
+      const volatile double *qb = (pb) ? (pb) + (long long)b * G : qa;                  \
+      for (int c = c_lo + gl; c <= c_hi; c += GW) { va += qa[c]; vb += qb[c]; }         \
+    }                                                                                   \
+    for (int o = GW >> 1; o > 0; o >>= 1) {                                             \
+      va += __shfl_xor_sync(0xffffffffu, va, o);                                        \
+      vb += __shfl_xor_sync(0xffffffffu, vb, o);                                        \
+    }                                                                                   \
+    if (b < B && gl == 0) { s_ta[b] = va; s_tb[b] = vb; }                               \
+    __syncthreads();                                                                    \
+  }
+
+  // ---- phase B of one macro-tile: r -= alpha Ap (skipped when !use_ap), z = M^-1 r by the staged IC sweeps;
+  //      thread (ty, tx) owns rows 8 ty .. 8 ty + 7, column tx of the macro-tile.  Accumulates r.z and r.r.
+#define PHASE_B_TILE(t, alpha_f, use_ap, acc_rz, acc_rr)                                                       \
+  {                                                                                                            \
+    const int tl = (int)((t) - tbase);                                                                         \
+    const int px = (tl % P.tiles_x) * IC_MWPX + (ty % IC_GX) * 32 + tx;                                        \
+    const int py0 = (tl / P.tiles_x) * IC_MHPX + (ty / IC_GX) * 8;                                             \
+    float2 rn[8];                                                                                              \
+    _Pragma("unroll")                                                                                          \
+    for (int hf = 0; hf < 2; ++hf) {                                                                           \
+      float2 rc[4], ac[4];                                                                                     \
+      uint2 wp[4];                                                                                             \
+      float m11[4], m12[4], m22[4];                                                                            \
+      bool ok[4];                                                                                              \
+      long long ii[4];                                                                                         \
+      _Pragma("unroll")                                                                                        \
+      for (int u = 0; u < 4; ++u) {                                                                            \
+        const int py = py0 + hf * 4 + u;                                                                       \
+        ok[u] = px < W && py < H;                                                                              \
+        ii[u] = ok[u] ? base + (long long)py * W + px : base;                                                  \
+        rc[u] = ldg_f2(r + ii[u]);                                                                             \
+        ac[u] = (use_ap) ? ldg_f2(Ap + ii[u]) : make_float2(0.f, 0.f);                                         \
+        m11[u] = ldg_nc_f(Minv + ii[u]); m12[u] = ldg_nc_f(Minv + n_all + ii[u]);                              \
+        m22[u] = ldg_nc_f(Minv + 2 * n_all + ii[u]);                                                           \
+        wp[u] = ldg_nc_u2(Wpk + ii[u]);                                                                        \
+      }                                                                                                        \
+      _Pragma("unroll")                                                                                        \
+      for (int u = 0; u < 4; ++u) {                                                                            \
+        const int row = ty * 8 + hf * 4 + u;                                                                   \
+        const int sl = ic_slot(row, tx);                                                                       \
+        float2 v = make_float2(0.f, 0.f);                                                                      \
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);                                                           \
+        unsigned cw = 0u;                                                                                      \
+        if (ok[u]) {                                                                                           \
+          v = (use_ap) ? make_float2(rc[u].x - (alpha_f) * ac[u].x, rc[u].y - (alpha_f) * ac[u].y) : rc[u];    \
+          if (use_ap) r[ii[u]] = v;                                                                            \
+          c0 = make_float4(m11[u], m12[u], m22[u], __uint_as_float(wp[u].x));                                  \
+          cw = (row & 7) == 7 ? 0u : wp[u].y;                                                                  \
+          acc_rr += (double)v.x * (double)v.x + (double)v.y * (double)v.y;                                     \
+        }                                                                                                      \
+        rn[hf * 4 + u] = v;                                                                                    \
+        sts64(sm.r + sl * 8, v); sts128(sm.c0 + sl * 16, c0); sts32(sm.cw + sl * 4, cw);                       \
+      }                                                                                                        \
+    }                                                                                                          \
+    ic_stage_sync();                                                                                           \
+    if (ty < IC_SWEEP_WARPS && !(P.debug & 1)) ic_sweeps(sm, ty, tx);                                          \
+    ic_stage_sync();                                                                                           \
+    _Pragma("unroll")                                                                                          \
+    for (int u = 0; u < 8; ++u) {                                                                              \
+      const int py = py0 + u;                                                                                  \
+      if (px < W && py < H) {                                                                                  \
+        const float2 zz = lds64(sm.r + ic_slot(ty * 8 + u, tx) * 8);                                           \
+        z[base + (long long)py * W + px] = zz;                                                                 \
+        acc_rz += (double)rn[u].x * (double)zz.x + (double)rn[u].y * (double)zz.y;                             \
+      }                                                                                                        \
+    }                                                                                                          \
+  }
+
+  // ---------------- init ----------------
+  for (int b = tid; b < MAXB; b += IC_THREADS) { s_state[b] = b < B ? 0 : 1; s_bad[b] = 0; s_flush[b] = 0; }
+  REMAP()
+  {
+    OWN_RANGE()
+    for (int a = a_first; a <= a_last; ++a) {
+      TILE_RANGE(a)
+      double acc_rz = 0.0, acc_bb = 0.0;
+      for (long long t = ta; t < tb; ++t) {
+        const int tl = (int)(t - tbase);
+        const int px = (tl % P.tiles_x) * IC_MWPX + (ty % IC_GX) * 32 + tx;
+        const int py0 = (tl / P.tiles_x) * IC_MHPX + (ty / IC_GX) * 8;
+#pragma unroll 2
+        for (int u = 0; u < 8; ++u) {
+          const int py = py0 + u;
+          const int sl = ic_slot(ty * 8 + u, tx);
+          float2 v = make_float2(0.f, 0.f);
+          float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          unsigned cw = 0u;
+          if (px < W && py < H) {
+            const long long i = base + (long long)py * W + px;
+            const Stencil s = load_stencil(S, i, px, py);
+            const double duu = s.d.x + s.wr.x + s.wl.x + s.wd.x + s.wu.x;
+            const double dvv = s.d.y + s.wr.y + s.wl.y + s.wd.y + s.wu.y;
+            const float2 fwh = make_float2((float)s.wr.x, (float)s.wr.y), fwv = make_float2((float)s.wd.x, (float)s.wd.y);
+            Df[i] = make_float2((float)s.d.x, (float)s.d.y);
+            a12f[i] = (float)s.a12;
+            WHf[i] = fwh;
+            WVf[i] = fwv;
+            const uint2 wp = make_uint2(ic_pack(fwh.x, fwh.y), ic_pack(fwv.x, fwv.y));
+            Wpk[i] = wp;
+            const double2 rb = __ldg(&S.rhs[i]);
+            v = make_float2((float)rb.x, (float)rb.y);
+            x[i] = make_double2(0.0, 0.0);
+            r[i] = v;
+            pold[i] = make_float2(0.f, 0.f);
+            y[i] = make_float2(0.f, 0.f);
+            c0 = make_float4((float)duu, (float)s.a12, (float)dvv, __uint_as_float(wp.x));
+            cw = (u == 7) ? 0u : wp.y;
+            acc_bb += rb.x * rb.x + rb.y * rb.y;
+          }
+          sts64(sm.r + sl * 8, v); sts128(sm.c0 + sl * 16, c0); sts32(sm.cw + sl * 4, cw);
+        }
+        ic_stage_sync();
+        if (ty < IC_SWEEP_WARPS) {
+          ic_factor(sm, ty, tx);
+          __syncwarp();
+          ic_sweeps(sm, ty, tx);
+        }
+        ic_stage_sync();
+#pragma unroll 2
+        for (int u = 0; u < 8; ++u) {
+          const int py = py0 + u;
+          if (px < W && py < H) {
+            const long long i = base + (long long)py * W + px;
+            const int sl = ic_slot(ty * 8 + u, tx);
+            const float2 zz = lds64(sm.r + sl * 8), rv = r[i];
+            const float4 c0 = lds128(sm.c0 + sl * 16);
+            z[i] = zz;
+            Minv[i] = c0.x; Minv[n_all + i] = c0.y; Minv[2 * n_all + i] = c0.z;
+            acc_rz += (double)rv.x * (double)zz.x + (double)rv.y * (double)zz.y;
+          }
+        }
+      }
+      ic_block_sum2(acc_rz, acc_bb, sm_red);
+      if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_bb; }
+    }
+  }
+  grid.sync();
+  REDUCE_ALL(part_b, part_c, 0)
+  if (tid < B) {
+    const int b = tid;
+    double rz = s_ta[b], bb = s_tb[b];
+    s_rz[b] = rz; s_bb[b] = bb; s_maxr2[b] = bb; s_alpha[b] = 0.0; s_beta[b] = 0.0; s_rzprev[b] = rz;
+    if (!(bb > 0.0) || !(rz > 0.0)) {                    // zero right-hand side: x = 0 is the solution
+      if (cta == C_LO(b)) { done_g[b] = 1; iters_g[b] = 0; relres_g[b] = 0.0; }
+      s_state[b] = 1;
+    }
+  }
+  REMAP()
+  int n_active = s_nact;
+
+#ifdef IC_TIMERS                                                 // tuning build: cycles per phase, printed by three CTAs
+  long long tmA = 0, tmS1 = 0, tmB = 0, tmS2 = 0, tm0 = 0;
+#define IC_TICK(acc) { const long long now = clock64(); acc += now - tm0; tm0 = now; }
+#else
+#define IC_TICK(acc)
+#endif
+  int k = 0;
+  for (; k < P.maxit && n_active > 0; ++k) {
+    OWN_RANGE()
+#ifdef IC_TIMERS
+    tm0 = clock64();
+#endif
+    // ---------------- phase A: p = z + beta p_old (on the fly), y += alpha_prev p_old, Ap = A p ----------------
+    for (int a = a_first; a <= a_last; ++a) {
+      TILE_RANGE(a)
+      const float beta = (float)s_beta[b], aprev = (float)s_alpha[b];
+      const double aprev_d = s_alpha[b];
+      const bool flush = s_flush[b] != 0;       // a reliable update happened: fold y + alpha p into the fp64 solution now
+      double acc = 0.0, dummy = 0.0;
+      for (long long v = ta * IC_SUBS; v < tb * IC_SUBS; v += IC_UA) {
+        int px[IC_UA], py[IC_UA]; long long i[IC_UA]; bool ok[IC_UA];
+        float2 zc[IC_UA], po[IC_UA], zl[IC_UA], pl[IC_UA], zr[IC_UA], pr[IC_UA], zu[IC_UA], pu[IC_UA], zd[IC_UA],
+            pd[IC_UA], sd[IC_UA], swr[IC_UA], swd[IC_UA], swl[IC_UA], swu[IC_UA], yc[IC_UA];
+        float sa12[IC_UA];
+#pragma unroll
+        for (int u = 0; u < IC_UA; ++u) {
+          PIXEL_OF(v + u, px[u], py[u], i[u], ok[u])
+          const long long ii = i[u];
+          const long long jl = ii > 0 ? ii - 1 : 0, jr = ii + 1 < n_all ? ii + 1 : n_all - 1;
+          const long long ju = ii >= W ? ii - W : 0, jd = ii + W < n_all ? ii + W : n_all - 1;
+          zc[u] = z[ii]; po[u] = pold[ii];
+          zl[u] = z[jl]; pl[u] = pold[jl]; zr[u] = z[jr]; pr[u] = pold[jr];
+          zu[u] = z[ju]; pu[u] = pold[ju]; zd[u] = z[jd]; pd[u] = pold[jd];
+          sd[u] = __ldg(&Df[ii]); swr[u] = __ldg(&WHf[ii]); swd[u] = __ldg(&WVf[ii]);
+          swl[u] = __ldg(&WHf[jl]); swu[u] = __ldg(&WVf[ju]);
+          sa12[u] = __ldg(&a12f[ii]);
+          yc[u] = y[ii];
+        }
+#pragma unroll
+        for (int u = 0; u < IC_UA; ++u) {
+          if (!ok[u]) continue;
+          const float2 c = make_float2(zc[u].x + beta * po[u].x, zc[u].y + beta * po[u].y);
+          float2 nl = make_float2(zl[u].x + beta * pl[u].x, zl[u].y + beta * pl[u].y);
+          float2 nr = make_float2(zr[u].x + beta * pr[u].x, zr[u].y + beta * pr[u].y);
+          float2 nu = make_float2(zu[u].x + beta * pu[u].x, zu[u].y + beta * pu[u].y);
+          float2 nd = make_float2(zd[u].x + beta * pd[u].x, zd[u].y + beta * pd[u].y);
+          if (px[u] == 0) nl = c;
+          if (px[u] + 1 >= W) nr = c;
+          if (py[u] == 0) nu = c;
+          if (py[u] + 1 >= H) nd = c;
+          float au = sd[u].x * c.x + sa12[u] * c.y;
+          float av = sa12[u] * c.x + sd[u].y * c.y;
+          au += swr[u].x * (c.x - nr.x); av += swr[u].y * (c.y - nr.y);
+          au += swl[u].x * (c.x - nl.x); av += swl[u].y * (c.y - nl.y);
+          au += swd[u].x * (c.x - nd.x); av += swd[u].y * (c.y - nd.y);
+          au += swu[u].x * (c.x - nu.x); av += swu[u].y * (c.y - nu.y);
+          if (flush) {
+            double2 xc = x[i[u]];
+            x[i[u]] = make_double2(xc.x + ((double)yc[u].x + aprev_d * (double)po[u].x),
+                                   xc.y + ((double)yc[u].y + aprev_d * (double)po[u].y));
+            y[i[u]] = make_float2(0.f, 0.f);
+          } else {
+            y[i[u]] = make_float2(yc[u].x + aprev * po[u].x, yc[u].y + aprev * po[u].y);
+          }
+          pnew[i[u]] = c;
+          Ap[i[u]] = make_float2(au, av);
+          acc += (double)c.x * (double)au + (double)c.y * (double)av;
+        }
+      }
+      ic_block_sum2(acc, dummy, sm_red);
+      if (tid == 0) part_a[(long long)b * G + cta] = acc;
+    }
+    IC_TICK(tmA)
+    grid.sync();
+    IC_TICK(tmS1)
+    REDUCE_ALL(part_a, (const double *)nullptr, 0)
+    if (tid < B && s_state[tid] == 0) {
+      double pap = s_ta[tid];
+      s_alpha[tid] = pap > 0.0 ? s_rz[tid] / pap : 0.0;      // 0 => breakdown, resolved by the reliable update below
+      s_flush[tid] = 0;
+    }
+    __syncthreads();
+    // ---------------- phase B: r -= alpha Ap, z = M^-1 r (tile-local IC sweeps), partial r.z and r.r ----------------
+    for (int a = a_first; a <= a_last; ++a) {
+      TILE_RANGE(a)
+      const float alpha = (float)s_alpha[b];
+      double acc_rz = 0.0, acc_rr = 0.0;
+      for (long long t = ta; t < tb; ++t) PHASE_B_TILE(t, alpha, true, acc_rz, acc_rr)
+      ic_block_sum2(acc_rz, acc_rr, sm_red);
+      if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
+    }
+    IC_TICK(tmB)
+    grid.sync();
+    IC_TICK(tmS2)
+    REDUCE_ALL(part_b, part_c, 0)
+    int rel = 0;
+    if (tid < B && s_state[tid] == 0) {
+      const int b = tid;
+      double rz = s_ta[b], rr = s_tb[b], alpha = s_alpha[b];
+      int bad = !(alpha > 0.0) || !(rz > 0.0) || !(rr == rr);
+      rel = bad || rr <= P.tol2 * s_bb[b] || rr < P.delta2 * s_maxr2[b] || k + 1 == P.maxit;
+      if (rel) {
+        s_state[b] = 3; s_bad[b] = bad; s_rzprev[b] = s_rz[b];
+      } else {
+        s_beta[b] = rz / s_rz[b];
+        s_rz[b] = rz;
+      }
+    }
+    if (__syncthreads_or(rel)) {
+      // ---------------- reliable update: r = b - A (x + y + alpha p) in fp64, then z = M^-1 r ----------------
+      for (int a = a_first; a <= a_last; ++a) {
+        TILE_RANGE(a)
+        if (s_state[b] != 3) continue;
+        const double alpha = s_alpha[b];
+        double acc_rz = 0.0, acc_rr = 0.0, acc_dummy = 0.0;
+        for (long long v = ta * IC_SUBS; v < tb * IC_SUBS; ++v) {
+          int px, py; long long i; bool ok;
+          PIXEL_OF(v, px, py, i, ok)
+          if (!ok) continue;
+          const double2 rt = ic_true_residual(P, i, px, py, pnew, alpha);
+          r[i] = make_float2((float)rt.x, (float)rt.y);
+          acc_rr += rt.x * rt.x + rt.y * rt.y;
+        }
+        __syncthreads();                       // r of the own macro-tiles is complete (same ownership in both passes)
+        for (long long t = ta; t < tb; ++t) PHASE_B_TILE(t, 0.f, false, acc_rz, acc_dummy)
+        ic_block_sum2(acc_rz, acc_rr, sm_red);
+        if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
+      }
+      grid.sync();
+      REDUCE_ALL(part_b, part_c, 3)
+      int fin = 0;
+      if (tid < B && s_state[tid] == 3) {
+        const int b = tid;
+        double rz = s_ta[b], rr = s_tb[b];
+        int conv = rr <= P.tol2 * s_bb[b];
+        if (conv || s_bad[b] || !(rz > 0.0) || !(rr == rr) || k + 1 == P.maxit) {
+          s_state[b] = 2;
+          fin = 1;
+          if (cta == C_LO(b)) {
+            done_g[b] = conv ? 1 : (k + 1 == P.maxit && !s_bad[b] ? 3 : 2);
+            iters_g[b] = k + 1;
+            relres_g[b] = sqrt(rr / s_bb[b]);
+          }
+        } else {
+          s_state[b] = 0;
+          s_flush[b] = 1;                                  // x += y + alpha_k p_k rides on the next phase A
+          s_maxr2[b] = rr;
+          s_beta[b] = rz / s_rzprev[b];
+          s_rz[b] = rz;
+        }
+      }
+      if (__syncthreads_or(fin)) {
+        // systems that just finished: fold the pending y + alpha p into x (own pixels only), then re-deal the tiles
+        for (int a = a_first; a <= a_last; ++a) {
+          TILE_RANGE(a)
+          if (s_state[b] != 2) continue;
+          const double alpha = s_alpha[b];
+          for (long long v = ta * IC_SUBS; v < tb * IC_SUBS; ++v) {
+            int px, py; long long i; bool ok;
+            PIXEL_OF(v, px, py, i, ok)
+            if (!ok) continue;
+            double2 xc = x[i];
+            float2 yc = y[i], pc = pnew[i];
+            x[i] = make_double2(xc.x + ((double)yc.x + alpha * (double)pc.x), xc.y + ((double)yc.y + alpha * (double)pc.y));
+          }
+        }
+        __syncthreads();
+        if (tid < B && s_state[tid] == 2) s_state[tid] = 1;
+        REMAP()
+        n_active = s_nact;
+      }
+    }
+    { float2 *t = pold; pold = pnew; pnew = t; }
+  }
+#ifdef IC_TIMERS
+  if (tid == 0 && (cta == 0 || cta == G / 2 || cta == G - 2))
+    printf("[ic timers] cta %d of %d, %d iterations: phase A %.1f, sync %.1f, phase B %.1f, sync %.1f kcycles/iter\n", cta, G, k,
+           1e-3 * tmA / k, 1e-3 * tmS1 / k, 1e-3 * tmB / k, 1e-3 * tmS2 / k);
+#endif
+#undef IC_TICK
+#undef REMAP
+#undef C_LO
+#undef C_HI
+#undef OWN_RANGE
+#undef REDUCE_ALL
+#undef TILE_RANGE
+#undef PIXEL_OF
+#undef PHASE_B_TILE
+}
+
+// two CTAs x (56 KB staged tile + 11 KB scalars + 1 KB reserved) = 138 KB -> the 164 KB shared-memory configuration, which
+// leaves 92 KB of L1 for phase A's stencil reuse (measured: below ~90 KB of L1 the matvec phase loses 35 %)
+constexpr int IC_CARVEOUT_PCT = 64;
+
+int pcg_ic_grid(b200flow_ctx *ctx, int *grid_out) {
+  static int cached_dev = -1, cached = 0;
+  if (cached_dev != ctx->device) {
+    int nb = 0;
+    BF_CUDA(ctx, cudaFuncSetAttribute(pcg_ic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IC_SMEM));
+    const char *cv = getenv("B200FLOW_IC_CARVEOUT");
+    BF_CUDA(ctx, cudaFuncSetAttribute(pcg_ic_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cv ? atoi(cv) : IC_CARVEOUT_PCT));
+    BF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcg_ic_kernel, IC_THREADS, IC_SMEM));
+    if (nb < 1) return set_err(ctx, B200FLOW_ECUDA, "pcg_ic_kernel cannot be made resident");
+    cached = nb * ctx->num_sms;
+    cached_dev = ctx->device;
+  }
+  *grid_out = cached;
+  return 0;
+}
+
+int k_pcg_ic_launch(b200flow_ctx *ctx, MixParams P, int grid_max) {
+  const LinSys &sys = P.sys;
+  if (sys.B > MAXB)
+    return set_err(ctx, B200FLOW_EINVAL, "batch of %d systems exceeds %d per solve; split the batch", sys.B, MAXB);
+  P.tiles_x = (int)cdiv(sys.W, IC_MWPX);
+  P.tiles_y = (int)cdiv(sys.H, IC_MHPX);
+  P.tiles_per_sys = P.tiles_x * P.tiles_y;
+  const long long total = (long long)P.tiles_per_sys * sys.B;
+  int G = grid_max;
+  if ((long long)G > total) G = (int)total;
+  if (G < 1) G = 1;
+  P.w.grid = G;
+  const char *dbg = getenv("B200FLOW_IC_DEBUG");
+  P.debug = dbg ? atoi(dbg) : 0;
+  void *args[] = {&P};
+  BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_ic_kernel, dim3(G), dim3(IC_THREADS), args, IC_SMEM, ctx->stream));
+  return 0;
+}
+
+}  // namespace bf

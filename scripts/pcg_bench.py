@@ -11,14 +11,14 @@ sys.path.insert(0, os.path.join(ROOT, "optical-flow-python_b200"))
 from optical_flow import _lib  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--solver", type=int, default=0, help="0 mixed fp32/fp64 (120 B/px/it), 2 all-fp64 (228 B/px/it)")
+ap.add_argument("--solver", type=int, default=4, help="4 mixed + tile-local IC(0) (128 B/px/it), 0 mixed block-Jacobi (120 B/px/it), 2 all-fp64 (228 B/px/it)")
 ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--cases", nargs="*", default=["16,480,640", "16,384,512", "16,240,320", "16,120,160", "16,60,80",
                                                 "16,30,40", "1,480,640", "4,2160,3840", "64,388,584"])
 args = ap.parse_args()
 ctx = _lib.default_context(0)
-bytes_px = {0: 120, 2: 228, 1: 228}[args.solver]
+bytes_px = {0: 120, 2: 228, 1: 228, 4: 128}[args.solver]
 for case in args.cases:
     B, H, W = [int(v) for v in case.split(",")]
     ms, it = C.c_double(0), C.c_longlong(0)

@@ -46,7 +46,7 @@ def test_hs_system(systems, stages):
 
 @pytest.mark.parametrize("tag,preset", [("ba", "ba"), ("cnl", "classic+nl"), ("cpp", "classic++"), ("cc", "classic-c")])
 @pytest.mark.parametrize("alpha", [1.0, 0.5, 0.0])
-@pytest.mark.parametrize("precision", ["mixed", "fp64"])
+@pytest.mark.parametrize("precision", ["mixed", "mixed-jacobi", "fp64"])
 def test_gnc_system(systems, tag, preset, alpha, precision):
     from optical_flow import load_of_method
     ope = load_of_method(preset)
@@ -94,7 +94,7 @@ def test_solver_precision_names():
         ope._apply_solver(ope._c_params())
 
 
-@pytest.mark.parametrize("precision", ["mixed", "fp64"])
+@pytest.mark.parametrize("precision", ["mixed", "mixed-jacobi", "fp64"])
 def test_pcg_determinism_and_batch(systems, precision):
     """Same system solved twice gives bit-identical x (fixed-order reductions, no fp atomics)."""
     from optical_flow import load_of_method
