@@ -29,7 +29,8 @@ struct LinSys {                // matrix-free 2N x 2N system, B systems of H x W
 struct PcgWork {               // scratch vectors + reduction buffers for the persistent PCG kernel
   double2 *r, *p, *p2, *z, *Ap; // residual, search direction (ping-pong), preconditioned residual, A p
   float *Minv;                 // 3 planes: m11, m12, m22 (block-Jacobi inverse / IC pivot inverse, fp32) [3][B*H*W]
-  uint2 *wpk;                  // IC preconditioner: edge weights as truncated bf16 pairs {wuh,wvh},{wuv,wvv} [B*H*W]
+  float4 *ic_c0;               // IC preconditioner [B*H*W]: {i11, i12, i22, bf16x2 {wuh, wvh}} (inverted pivot block + right edge)
+  unsigned *ic_cw;             // IC preconditioner [B*H*W]: bf16x2 {wuv, wvv} (down edge; 0 on every eighth row)
   double *partial;             // [3][B][grid]
   double *scal;                // per-system scalars [8][B]
   int *flags;                  // [0]=ndone, [1..B]=done[b], then iters[b]

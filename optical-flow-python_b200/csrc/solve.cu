@@ -804,7 +804,7 @@ __global__ void pcg_stats_kernel(const int *flags, int B, long long hw, long lon
 
 size_t pcg_work_bytes(const b200flow_ctx *ctx, int B, int H, int W) {
   size_t n = (size_t)B * H * W;
-  return n * (5 * sizeof(double2) + 3 * sizeof(float) + sizeof(uint2)) + 4 * (size_t)B * ctx->num_sms * 8 * 8 + 64 * B + 4096;
+  return n * (5 * sizeof(double2) + 3 * sizeof(float) + sizeof(float4) + sizeof(unsigned)) + 4 * (size_t)B * ctx->num_sms * 8 * 8 + 64 * B + 4096;
 }
 
 static int pcg_grid(b200flow_ctx *ctx, int *grid_out, int *grid_mixed_out) {
@@ -838,7 +838,8 @@ int pcg_work_alloc(b200flow_ctx *ctx, int B, int H, int W, PcgWork *w) {
   BF_TRY(arena_alloc(ctx, &w->z, n));
   BF_TRY(arena_alloc(ctx, &w->Ap, n));
   BF_TRY(arena_alloc(ctx, &w->Minv, 3 * n));
-  BF_TRY(arena_alloc(ctx, &w->wpk, n));
+  BF_TRY(arena_alloc(ctx, &w->ic_c0, n));
+  BF_TRY(arena_alloc(ctx, &w->ic_cw, n));
   BF_TRY(arena_alloc(ctx, &w->partial, (size_t)4 * B * G));   // G = the larger of the two kernels' grids
   BF_TRY(arena_alloc(ctx, &w->scal, (size_t)B));
   BF_TRY(arena_alloc(ctx, &w->flags, (size_t)(1 + 2 * B)));

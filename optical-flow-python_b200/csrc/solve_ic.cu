@@ -15,7 +15,7 @@
 //
 // Algorithmic bytes per pixel-iteration (fp32 working set):
 //   A  read z 8, p_old 8, y 8, D 8, a12 4, WH 8, WV 8; write p 8, y 8, Ap 8                              = 76
-//   B  read r 8, Ap 8, P^-1 12, edges as 4 truncated bf16 8; write r 8, z 8                               = 52
+//   B  read r 8, Ap 8, {P^-1 12, 4 edge weights as truncated bf16 8} by cp.async; write r 8, z 8          = 52
 //                                                                                            total        128 B
 // Everything else (all-system scalar tracking, re-dealing of the active tiles, reliable updates on the fp64 true
 // residual, determinism) is as in pcg_mixed_kernel.
@@ -29,36 +29,35 @@ namespace bf {
 #define IC_THREADS 256                         // threads per CTA: 256 (2 CTAs / SM) or 128 (4 CTAs / SM)
 #endif
 constexpr int IC_TH = IC_THREADS / 32;         // rows of one 32 x IC_TH thread tile (phase A: one pixel per thread)
-constexpr int IC_MW = 32, IC_MH = IC_TH * 8;   // macro-tile (pixels) staged in shared memory: every thread owns 8 rows x 1 column
-constexpr int IC_NPIX = IC_MW * IC_MH;
-// Footprint of a macro-tile in the IMAGE: its IC_THREADS / 32 strips of 8 rows x 32 columns (one per warp in phase B)
-// are laid out IC_GX across, so that a macro-tile row is IC_GX * 256 contiguous bytes of every float2 stream (whole
-// DRAM pages) instead of eight 256-byte pieces of eight different rows.  IC_GX = 1 is the vertical 64 x 32 stack.
+constexpr int IC_NSTRIP = IC_THREADS / 32;     // strips (8 rows x 32 columns) per macro-tile: one per warp in phase B
+constexpr int IC_ROWS = IC_NSTRIP * 8;         // staged rows
+constexpr int IC_PITCH = 34;                   // staged row pitch in elements (see ic_slot)
+constexpr int IC_PAD = 8;                      // guard elements before / after each staged array (idle wavefront steps)
+constexpr int IC_NSLOT = IC_ROWS * IC_PITCH + 2 * IC_PAD;
+// Footprint of a macro-tile in the IMAGE: its strips are laid out IC_GX across, so that a macro-tile row is
+// IC_GX * 256 contiguous bytes of every float2 stream.  IC_GX = 1 is a vertical stack of strips.
 #ifndef IC_GX
-#define IC_GX 4
+#define IC_GX 2
 #endif
-constexpr int IC_NSTRIP = IC_THREADS / 32;
 constexpr int IC_GY = IC_NSTRIP / IC_GX;
 constexpr int IC_MWPX = 32 * IC_GX, IC_MHPX = 8 * IC_GY;
 static_assert(IC_GX * IC_GY == IC_NSTRIP, "strips must tile the macro-tile");
-constexpr int IC_SUBH = 8;                     // sub-tile height (rows coupled by the incomplete factor)
-#ifndef IC_SW
-#define IC_SW 8                                // sub-tile width: 8, 16 or 32 (scripts/ic32_proto.py: 231 / 212 / 211 iterations)
+constexpr int IC_SW = 8;                       // sub-tile = 8 rows x 8 columns (scripts/ic32_proto.py: 231 iterations vs 470)
+constexpr int IC_STEPS = IC_SW + 8 - 1;        // anti-diagonals of one sub-tile
+#ifndef IC_SWEEP_UNROLL_N
+#define IC_SWEEP_UNROLL_N 5                     // of the 15 wavefront steps (a full unroll exhausts the 7 predicate registers)
 #endif
-static_assert(IC_GX == 1 || IC_SW == 8, "the horizontal layout needs warp-independent 8 x 8 sub-tiles");
-constexpr int IC_STEPS = IC_SW + IC_SUBH - 1;  // anti-diagonals of one sub-tile
-constexpr int IC_SWEEP_WARPS = IC_MH / IC_SW;  // lanes needed = IC_MH rows x (32 / IC_SW) column blocks
-constexpr int IC_SUBS = IC_MH / IC_TH;         // 32 x IC_TH thread tiles per macro-tile (= 8)
+constexpr int IC_SWEEP_UNROLL = IC_SWEEP_UNROLL_N;
+constexpr int IC_SUBS = 8;                     // 32 x IC_TH thread tiles per macro-tile
 // staged per pixel: float4 {i11, i12, i22, bf16x2 {wuh, wvh}} + bf16x2 {wuv, wvv} + float2 r = 28 B
-constexpr size_t IC_SMEM = (size_t)IC_NPIX * (sizeof(float4) + sizeof(unsigned) + sizeof(float2));   // 56 KB
+constexpr size_t IC_SMEM = (size_t)IC_NSLOT * (sizeof(float4) + sizeof(unsigned) + sizeof(float2));   // 60 KB at 256 threads
 
-// shared-memory slot of macro-tile pixel (row, col): every row is rotated by
-//   sigma(row) = 2 (row mod 8) + 8 ((row / 8) mod (IC_SW / 8))
-// so that both access patterns are bank-conflict free for 4-, 8- and 16-byte elements: a warp touching one row
-// (lane = column), and a warp walking the anti-diagonals of its four sub-tiles (lane = (sub-tile q, row j), column =
-// column block + step - j): the physical column is then (step + lane + const) mod 32.
-__device__ __forceinline__ int ic_sigma(int row) { return 2 * (row & 7) + 8 * ((row >> 3) & (IC_SW / 8 - 1)); }
-__device__ __forceinline__ int ic_slot(int row, int col) { return row * IC_MW + ((col + ic_sigma(row)) & 31); }
+// Shared-memory slot of staged pixel (row, col), row = 8 * strip + j.  A pitch of 34 elements makes both access patterns
+// bank-conflict free for 4-, 8- and 16-byte elements without any index arithmetic in the wavefront: a warp touching one
+// row (lane = column), and a warp walking the anti-diagonals of its four 8 x 8 sub-tiles (lane = (sub-tile q, row j),
+// column 8 q + step - j): slot = const + 33 j + 8 q + step, i.e. (j + 8 q + step) mod 32 -- and `step` enters as a
+// compile-time immediate of the unrolled loop.
+__device__ __forceinline__ int ic_slot(int row, int col) { return IC_PAD + row * IC_PITCH + col; }
 
 // edge weights are kept as truncated bfloat16 pairs in the preconditioner (never in the operator): rounding TOWARDS
 // ZERO keeps the perturbed matrix a diagonally dominant M-matrix, so the incomplete factorisation still exists, and the
@@ -71,7 +70,7 @@ __device__ __forceinline__ float ic_lo(unsigned p) { return __uint_as_float(p <<
 __device__ __forceinline__ float ic_hi(unsigned p) { return __uint_as_float(p & 0xffff0000u); }
 
 // ---- shared-memory access by 32-bit shared-space address (computed once per kernel): keeps the generic-to-shared
-//      window arithmetic (an S2R of the cluster CTA id per access) out of the latency-bound wavefront loops
+//      window arithmetic (an S2R of the cluster CTA id per access) out of the wavefront loops
 __device__ __forceinline__ float4 lds128(unsigned a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
@@ -97,34 +96,9 @@ __device__ __forceinline__ void sts32(unsigned a, unsigned v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-// block-wide sum of two accumulators over IC_THREADS threads; result valid in thread 0
-__device__ __forceinline__ void ic_block_sum2(double &a, double &b, double (*sm)[IC_THREADS / 32]) {
-  a = warp_sum(a);
-  b = warp_sum(b);
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();   // protect sm reuse
-  if (l == 0) { sm[0][w] = a; sm[1][w] = b; }
-  __syncthreads();
-  if (w == 0) {
-    a = l < IC_THREADS / 32 ? sm[0][l] : 0.0;
-    b = l < IC_THREADS / 32 ? sm[1][l] : 0.0;
-    a = warp_sum(a);
-    b = warp_sum(b);
-  }
-}
-
-// With 8 x 8 sub-tiles the four sub-tiles a warp sweeps are exactly the 8 x 32 strip the same warp stages (thread
-// (ty, tx) owns rows 8 ty .. 8 ty + 7 of column tx), so the warps of a CTA never exchange data in phase B: a warp
-// barrier replaces the two block barriers and the 16 warps of an SM drift apart, overlapping one warp's global loads
-// with another's sweep.
-__device__ __forceinline__ void ic_stage_sync() {
-  if (IC_SW == 8) __syncwarp(); else __syncthreads();
-}
-
 // global loads of phase B as volatile asm: the compiler otherwise sinks each load down to its first use to save
-// registers (the kernel sits at the 128-register cap), which turned one batch of 24 loads per half-tile into seven
-// dependent round trips to DRAM (ncu: seven long-scoreboard stall points per tile).  Volatile asm statements keep their
-// program order, so the whole batch is in flight before the first value is consumed.
+// registers (the kernel sits at the 128-register cap), which turns one batch of loads per half-tile into several
+// dependent round trips to DRAM.  Volatile asm statements keep their program order.
 __device__ __forceinline__ float2 ldg_f2(const float2 *p) {
   float2 v;
   asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
@@ -141,112 +115,124 @@ __device__ __forceinline__ uint2 ldg_nc_u2(const uint2 *p) {
   return v;
 }
 
+// asynchronous global -> shared copies (LDGSTS): the preconditioner's coefficients go straight into the staged tile without
+// passing through registers; src_bytes = 0 zero-fills the destination (pixels outside the image)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// block-wide sum of two accumulators over IC_THREADS threads; result valid in thread 0
+__device__ __forceinline__ void ic_block_sum2(double &a, double &b, double (*sm)[IC_THREADS / 32]) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();   // protect sm reuse
+  if (l == 0) { sm[0][w] = a; sm[1][w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    a = l < IC_THREADS / 32 ? sm[0][l] : 0.0;
+    b = l < IC_THREADS / 32 ? sm[1][l] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+}
+
 struct IcSmem {            // shared-space byte addresses of the three staged arrays
   unsigned c0, cw, r;      // float4 {i11, i12, i22, bf16x2 wh}, bf16x2 wv, float2 r -> t -> z
 };
 
-// which sub-tile row this lane sweeps: warp w, lane (q = lane / 8, j = lane % 8) -> macro-tile row and first column
-struct IcLane { int row, col0; };
-__device__ __forceinline__ IcLane ic_lane(int w, int lane) {
-  const int q = lane >> 3, j = lane & 7;
-  int rb, cb;
-  if (IC_SW == 32) { rb = 4 * w + q; cb = 0; }
-  else if (IC_SW == 16) { rb = 2 * w + (q & 1); cb = q >> 1; }
-  else { rb = w; cb = q; }
-  IcLane L;
-  L.row = 8 * rb + j;
-  L.col0 = cb * IC_SW;
-  return L;
-}
-
-// ---- wavefront sweeps; executed by warps 0 .. IC_SWEEP_WARPS-1 ------------------------------------------------------
-// forward (P + L) t = r, backward (I + P^-1 L^T) z = t; r -> t -> z in place.  The down-edge weights {wuv, wvv} of
-// every sub-tile's LAST row are staged as 0, which cuts the coupling between sub-tiles without a select in the
-// dependent chain; the neighbour row is read with a rotating shuffle (lane 0 <- lane 31 is such a last row).  The
-// recurrences are arranged so that only two dependent FMAs follow each shuffle: everything that does not depend on
-// the shuffled value (products of coefficients, the own-row carry) is formed while the shuffle is in flight.
+// ---- wavefront sweeps of one strip (8 rows x 32 columns = four 8 x 8 sub-tiles) by the warp that staged it ----------
+// forward (P + L) t = r, backward (I + P^-1 L^T) z = t, in place (r -> t -> z).  Lane (q, j) walks row j of sub-tile q:
+// at step s it is at column s - j of the sub-tile, so the rows of a sub-tile form a wavefront and the neighbour row's
+// value arrives by a warp shuffle of the previous step.  Phase B is bound by instruction issue, not by latency (all 16
+// warps of an SM sweep concurrently), so the loops are fully unrolled (shared-memory offsets become immediates), carry
+// no masking arithmetic and no address arithmetic:
+//  * idle steps (column outside 0..7) read guard / neighbouring slots and compute garbage that nobody consumes: an
+//    active lane only ever reads the shuffle of a lane that was active at the same column one step earlier, and the
+//    own-row carries (cu, cv / zu, zv) and the store are predicated on the step being active;
+//  * the coupling between vertically adjacent sub-tiles is cut by the down-edge weights {wuv, wvv} of every eighth row
+//    being 0 (staged as 0, and forced to 0 on that row's idle steps), so what those rows push down is always 0 (the
+//    shuffle rotates, lane 0 <- lane 31 is such a row);
+//  * guard slots and the two pad columns are zeroed once per kernel, so idle-step garbage is always finite.
 __device__ __forceinline__ void ic_sweeps(const IcSmem sm, int w, int lane) {
   const unsigned full = 0xffffffffu;
-  const IcLane L = ic_lane(w, lane);
-  const int j = lane & 7;
+  const int q = lane >> 3, j = lane & 7;
   const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
-  const int rb = L.row * IC_MW;
-  const int x0 = L.col0 + ic_sigma(L.row);               // physical column of logical column c: (x0 + c) & 31
+  const int slot0 = ic_slot(8 * w + j, 8 * q - j);       // slot of step 0 (column -j); step s is slot0 + s
+  const unsigned a0 = sm.c0 + slot0 * 16, ar = sm.r + slot0 * 8, aw = sm.cw + slot0 * 4;
+  const unsigned actmask = 0xffu << j;                   // bit s set: step s is inside the sub-tile
+  const unsigned keep = j == 7 ? 0u : 0xffffffffu;       // last row of a sub-tile never pushes down / pulls up
   {
-    float cu = 0.f, cv = 0.f, pu = 0.f, pv = 0.f;      // pushed from the left (own row) / pushed down to the next row
-    int c = -j;
-    int idx = rb + ((x0 + c) & 31);
-    float2 R = lds64(sm.r + idx * 8);
-    float4 A = lds128(sm.c0 + idx * 16);
-    unsigned Wv = lds32(sm.cw + idx * 4);
-#pragma unroll 1
+    float cu = 0.f, cv = 0.f, pu = 0.f, pv = 0.f;        // pushed from the left (own row) / pushed down to the next row
+    float4 A = lds128(a0);
+    float2 R = lds64(ar);
+    unsigned Wv = lds32(aw);
+#pragma unroll IC_SWEEP_UNROLL
     for (int s = 0; s < IC_STEPS; ++s) {
-      const int idn = rb + ((x0 + c + 1) & 31);          // prefetch the next column (address independent of the chain)
-      const float2 Rn = lds64(sm.r + idn * 8);
-      const float4 An = lds128(sm.c0 + idn * 16);
-      const unsigned Wvn = lds32(sm.cw + idn * 4);
+      float4 An = A; float2 Rn = R; unsigned Wvn = Wv;
+      if (s + 1 < IC_STEPS) { An = lds128(a0 + (s + 1) * 16); Rn = lds64(ar + (s + 1) * 8); Wvn = lds32(aw + (s + 1) * 4); }
       const float uu = __shfl_sync(full, pu, up_lane), uw = __shfl_sync(full, pv, up_lane);
-      const bool act = (unsigned)c < (unsigned)IC_SW;
-      const unsigned m = act ? 0xffffffffu : 0u;         // idle step (column outside the sub-tile): pushes nothing
-      const unsigned wh = __float_as_uint(A.w) & m, wv = Wv & m;
-      const float whu = ic_lo(wh), whv = ic_hi(wh), wvu = ic_lo(wv), wvv = ic_hi(wv);
-      const float bu = R.x + cu, bv = R.y + cv;
-      const float su = fmaf(A.x, bu, A.y * bv), sv = fmaf(A.y, bu, A.z * bv);     // t without the row above
-      const float kuu = wvu * A.x, kuw = wvu * A.y, kvu = wvv * A.y, kvw = wvv * A.z;
-      pu = fmaf(kuu, uu, fmaf(kuw, uw, wvu * su));       // = wuv * t_u   (critical chain: shuffle -> 2 FMA -> shuffle)
-      pv = fmaf(kvu, uu, fmaf(kvw, uw, wvv * sv));       // = wvv * t_v
-      const float tu = fmaf(A.x, uu, fmaf(A.y, uw, su)), tv = fmaf(A.y, uu, fmaf(A.z, uw, sv));
-      cu = whu * tu; cv = whv * tv;
-      if (act) sts64(sm.r + idx * 8, make_float2(tu, tv));
-      R = Rn; A = An; Wv = Wvn; idx = idn; ++c;
+      unsigned am = actmask;
+      asm volatile("" : "+r"(am));                     // keeps the 15 step predicates from being hoisted (7 predicate registers)
+      const bool act = (am >> s) & 1u;
+      const float su = (R.x + cu) + uu, sv = (R.y + cv) + uw;
+      const float tu = fmaf(A.y, sv, A.x * su), tv = fmaf(A.z, sv, A.y * su);
+      const unsigned wh = __float_as_uint(A.w);
+      const unsigned wv = Wv & keep;
+      pu = ic_lo(wv) * tu; pv = ic_hi(wv) * tv;
+      if (act) {
+        cu = ic_lo(wh) * tu; cv = ic_hi(wh) * tv;
+        sts64(ar + s * 8, make_float2(tu, tv));
+      }
+      A = An; R = Rn; Wv = Wvn;
     }
   }
   {
-    float zu = 0.f, zv = 0.f;                            // own z of the previous step = right neighbour, offered to the row above
-    int c = IC_STEPS - 1 - j;
-    int idx = rb + ((x0 + c) & 31);
-    float2 Tr = lds64(sm.r + idx * 8);
-    float4 A = lds128(sm.c0 + idx * 16);
-    unsigned Wv = lds32(sm.cw + idx * 4);
-#pragma unroll 1
+    float zu = 0.f, zv = 0.f;                            // own z of the last active step = right neighbour, offered to the row above
+    float4 A = lds128(a0 + (IC_STEPS - 1) * 16);
+    float2 T = lds64(ar + (IC_STEPS - 1) * 8);
+    unsigned Wv = lds32(aw + (IC_STEPS - 1) * 4);
+#pragma unroll IC_SWEEP_UNROLL
     for (int s = IC_STEPS - 1; s >= 0; --s) {
-      const int idn = rb + ((x0 + c - 1) & 31);
-      const float2 Tn = lds64(sm.r + idn * 8);
-      const float4 An = lds128(sm.c0 + idn * 16);
-      const unsigned Wvn = lds32(sm.cw + idn * 4);
+      float4 An = A; float2 Tn = T; unsigned Wvn = Wv;
+      if (s > 0) { An = lds128(a0 + (s - 1) * 16); Tn = lds64(ar + (s - 1) * 8); Wvn = lds32(aw + (s - 1) * 4); }
       const float du = __shfl_sync(full, zu, dn_lane), dv = __shfl_sync(full, zv, dn_lane);
-      const bool act = (unsigned)c < (unsigned)IC_SW;
-      const unsigned m = act ? 0xffffffffu : 0u;         // idle step: z = 0
-      const unsigned wh = __float_as_uint(A.w) & m, wv = Wv & m;
-      const float whu = ic_lo(wh), whv = ic_hi(wh), wvu = ic_lo(wv), wvv = ic_hi(wv);
-      const float2 T = make_float2(__uint_as_float(__float_as_uint(Tr.x) & m), __uint_as_float(__float_as_uint(Tr.y) & m));
+      unsigned am = actmask;
+      asm volatile("" : "+r"(am));
+      const bool act = (am >> s) & 1u;
+      const unsigned wh = __float_as_uint(A.w);
       // z = T + P^-1 (WH z_right + WV z_down), z_right = own previous z
-      const float bu = fmaf(A.x * whu, zu, fmaf(A.y * whv, zv, T.x));
-      const float bv = fmaf(A.y * whu, zu, fmaf(A.z * whv, zv, T.y));
-      const float kuu = A.x * wvu, kuw = A.y * wvv, kvu = A.y * wvu, kvw = A.z * wvv;
-      zu = fmaf(kuu, du, fmaf(kuw, dv, bu));
-      zv = fmaf(kvu, du, fmaf(kvw, dv, bv));
-      if (act) sts64(sm.r + idx * 8, make_float2(zu, zv));
-      Tr = Tn; A = An; Wv = Wvn; idx = idn; --c;
+      const unsigned wv = Wv & keep;
+      const float au = fmaf(ic_lo(wv), du, ic_lo(wh) * zu), av = fmaf(ic_hi(wv), dv, ic_hi(wh) * zv);
+      const float nu = T.x + fmaf(A.y, av, A.x * au), nv = T.y + fmaf(A.z, av, A.y * au);
+      if (act) {
+        zu = nu; zv = nv;
+        sts64(ar + s * 8, make_float2(nu, nv));
+      }
+      A = An; T = Tn; Wv = Wvn;
     }
   }
 }
 
-// incomplete factorisation of the staged macro-tile: c0 holds {a11 + sum w_u, a12, a22 + sum w_v, wh} on entry and the
-// inverted pivot blocks {i11, i12, i22, wh} on exit.  Same wavefront as the sweeps (three pushed values per direction).
+// incomplete factorisation of the staged strip: c0 holds {a11 + sum w_u, a12, a22 + sum w_v, wh} on entry and the
+// inverted pivot blocks {i11, i12, i22, wh} on exit.  Same wavefront as the sweeps (three pushed values per direction);
+// runs once per solve, so it keeps a rolled loop and explicit masking.
 __device__ __forceinline__ void ic_factor(const IcSmem sm, int w, int lane) {
   const unsigned full = 0xffffffffu;
-  const IcLane L = ic_lane(w, lane);
-  const int j = lane & 7;
+  const int q = lane >> 3, j = lane & 7;
   const int up_lane = (lane + 31) & 31;
-  const int rb = L.row * IC_MW;
-  const int x0 = L.col0 + ic_sigma(L.row);
+  const int slot0 = ic_slot(8 * w + j, 8 * q - j);
   float c11 = 0.f, c12 = 0.f, c22 = 0.f, p11 = 0.f, p12 = 0.f, p22 = 0.f;
-  int c = -j;
 #pragma unroll 1
-  for (int s = 0; s < IC_STEPS; ++s, ++c) {
-    const bool act = (unsigned)c < (unsigned)IC_SW;
-    const int idx = rb + ((x0 + c) & 31);
+  for (int s = 0; s < IC_STEPS; ++s) {
+    const bool act = (unsigned)(s - j) < (unsigned)IC_SW;
+    const int idx = slot0 + s;
     const float4 A = lds128(sm.c0 + idx * 16);
     const unsigned wh = __float_as_uint(A.w), wv = lds32(sm.cw + idx * 4);
     const float whu = ic_lo(wh), whv = ic_hi(wh), wvu = ic_lo(wv), wvv = ic_hi(wv);
@@ -331,8 +317,10 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   IcSmem sm;
   sm.c0 = (unsigned)__cvta_generic_to_shared(ic_smem);             // float4 {i11, i12, i22, bf16x2 {wuh, wvh}}
   asm volatile("mov.u32 %0, %0;" : "+r"(sm.c0));                   // opaque: must live in a register, never rematerialised
-  sm.r = sm.c0 + IC_NPIX * 16;                                     // float2 r -> t -> z
-  sm.cw = sm.r + IC_NPIX * 8;                                      // bf16x2 {wuv, wvv}
+  sm.r = sm.c0 + IC_NSLOT * 16;                                    // float2 r -> t -> z
+  sm.cw = sm.r + IC_NSLOT * 8;                                     // bf16x2 {wuv, wvv}
+  for (int i = threadIdx.x; i < (int)(IC_SMEM / 4); i += IC_THREADS) sts32(sm.c0 + i * 4, 0u);   // guards / pad columns = 0
+  __syncthreads();
 
   __shared__ double sm_red[2][IC_THREADS / 32];
   __shared__ double s_rz[MAXB], s_bb[MAXB], s_alpha[MAXB], s_beta[MAXB], s_maxr2[MAXB], s_rzprev[MAXB];
@@ -345,12 +333,12 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   double *part_a = P.w.partial;                         // [B][G]  p.Ap
   double *part_b = P.w.partial + (long long)B * G;      // [B][G]  r.z
   double *part_c = P.w.partial + 2LL * B * G;           // [B][G]  r.r
-  float *Minv = P.w.Minv;                               // [3][n_all] inverted IC pivot blocks
+  float4 *C0 = P.w.ic_c0;                               // [n_all] {i11, i12, i22, bf16x2 {wuh, wvh}}: inverted IC pivot blocks + edges
+  unsigned *CW = P.w.ic_cw;                             // [n_all] bf16x2 {wuv, wvv}
   float2 *r = P.m.r, *z = P.m.z, *Ap = P.m.Ap, *y = P.m.y;
   float2 *pold = P.m.p, *pnew = P.m.p2;
   float2 *Df = P.m.D, *WHf = P.m.WH, *WVf = P.m.WV;
   float *a12f = P.m.a12;
-  uint2 *Wpk = P.w.wpk;                                 // bf16 pairs {wuh, wvh}, {wuv, wvv}: the preconditioner's copy of the edges
   double2 *x = P.x;
   int *done_g = P.w.flags + 1;
   int *iters_g = P.w.flags + 1 + B;
@@ -414,62 +402,56 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
     __syncthreads();                                                                    \
   }
 
-  // ---- phase B of one macro-tile: r -= alpha Ap (skipped when !use_ap), z = M^-1 r by the staged IC sweeps;
-  //      thread (ty, tx) owns rows 8 ty .. 8 ty + 7, column tx of the macro-tile.  Accumulates r.z and r.r.
+  // ---- phase B of one macro-tile: r -= alpha Ap (skipped when !use_ap), z = M^-1 r by the staged IC sweeps.  Thread
+  //      (ty, tx) owns rows 0 .. 7 of column tx of strip ty; a warp stages, sweeps and writes back its strip on its own
+  //      (warp barriers only), so the 16 warps of an SM overlap each other's loads and sweeps.  ONE round trip to
+  //      memory per tile: the coefficients travel global -> shared asynchronously (cp.async, no registers) while
+  //      r and Ap of all eight pixels are in flight in registers.  Accumulates r.z and r.r (fp32 over the thread's
+  //      eight pixels, fp64 across tiles).
 #define PHASE_B_TILE(t, alpha_f, use_ap, acc_rz, acc_rr)                                                       \
   {                                                                                                            \
     const int tl = (int)((t) - tbase);                                                                         \
     const int px = (tl % P.tiles_x) * IC_MWPX + (ty % IC_GX) * 32 + tx;                                        \
     const int py0 = (tl / P.tiles_x) * IC_MHPX + (ty / IC_GX) * 8;                                             \
-    float2 rn[8];                                                                                              \
-    _Pragma("unroll")                                                                                          \
-    for (int hf = 0; hf < 2; ++hf) {                                                                           \
-      float2 rc[4], ac[4];                                                                                     \
-      uint2 wp[4];                                                                                             \
-      float m11[4], m12[4], m22[4];                                                                            \
-      bool ok[4];                                                                                              \
-      long long ii[4];                                                                                         \
-      _Pragma("unroll")                                                                                        \
-      for (int u = 0; u < 4; ++u) {                                                                            \
-        const int py = py0 + hf * 4 + u;                                                                       \
-        ok[u] = px < W && py < H;                                                                              \
-        ii[u] = ok[u] ? base + (long long)py * W + px : base;                                                  \
-        rc[u] = ldg_f2(r + ii[u]);                                                                             \
-        ac[u] = (use_ap) ? ldg_f2(Ap + ii[u]) : make_float2(0.f, 0.f);                                         \
-        m11[u] = ldg_nc_f(Minv + ii[u]); m12[u] = ldg_nc_f(Minv + n_all + ii[u]);                              \
-        m22[u] = ldg_nc_f(Minv + 2 * n_all + ii[u]);                                                           \
-        wp[u] = ldg_nc_u2(Wpk + ii[u]);                                                                        \
-      }                                                                                                        \
-      _Pragma("unroll")                                                                                        \
-      for (int u = 0; u < 4; ++u) {                                                                            \
-        const int row = ty * 8 + hf * 4 + u;                                                                   \
-        const int sl = ic_slot(row, tx);                                                                       \
-        float2 v = make_float2(0.f, 0.f);                                                                      \
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);                                                           \
-        unsigned cw = 0u;                                                                                      \
-        if (ok[u]) {                                                                                           \
-          v = (use_ap) ? make_float2(rc[u].x - (alpha_f) * ac[u].x, rc[u].y - (alpha_f) * ac[u].y) : rc[u];    \
-          if (use_ap) r[ii[u]] = v;                                                                            \
-          c0 = make_float4(m11[u], m12[u], m22[u], __uint_as_float(wp[u].x));                                  \
-          cw = (row & 7) == 7 ? 0u : wp[u].y;                                                                  \
-          acc_rr += (double)v.x * (double)v.x + (double)v.y * (double)v.y;                                     \
-        }                                                                                                      \
-        rn[hf * 4 + u] = v;                                                                                    \
-        sts64(sm.r + sl * 8, v); sts128(sm.c0 + sl * 16, c0); sts32(sm.cw + sl * 4, cw);                       \
-      }                                                                                                        \
-    }                                                                                                          \
-    ic_stage_sync();                                                                                           \
-    if (ty < IC_SWEEP_WARPS && !(P.debug & 1)) ic_sweeps(sm, ty, tx);                                          \
-    ic_stage_sync();                                                                                           \
+    const long long i0 = base + (long long)py0 * W + px;                                                       \
+    const int sl0 = ic_slot(ty * 8, tx);                                                                       \
+    float2 rc[8], ac[8];                                                                                       \
     _Pragma("unroll")                                                                                          \
     for (int u = 0; u < 8; ++u) {                                                                              \
-      const int py = py0 + u;                                                                                  \
-      if (px < W && py < H) {                                                                                  \
-        const float2 zz = lds64(sm.r + ic_slot(ty * 8 + u, tx) * 8);                                           \
-        z[base + (long long)py * W + px] = zz;                                                                 \
-        acc_rz += (double)rn[u].x * (double)zz.x + (double)rn[u].y * (double)zz.y;                             \
+      const bool ok = px < W && py0 + u < H;                                                                   \
+      const long long ii = ok ? i0 + (long long)u * W : base;                                                  \
+      cp_async16(sm.c0 + (sl0 + u * IC_PITCH) * 16, C0 + ii, ok ? 16 : 0);                                     \
+      cp_async4(sm.cw + (sl0 + u * IC_PITCH) * 4, CW + ii, ok ? 4 : 0);                                        \
+      rc[u] = ldg_f2(r + ii);                                                                                  \
+      ac[u] = (use_ap) ? ldg_f2(Ap + ii) : make_float2(0.f, 0.f);                                              \
+    }                                                                                                          \
+    float prr = 0.f, prz = 0.f;                                                                                \
+    _Pragma("unroll")                                                                                          \
+    for (int u = 0; u < 8; ++u) {                                                                              \
+      const bool ok = px < W && py0 + u < H;                                                                   \
+      float2 v = make_float2(0.f, 0.f);                                                                        \
+      if (ok) {                                                                                                \
+        v = (use_ap) ? make_float2(fmaf(-(alpha_f), ac[u].x, rc[u].x), fmaf(-(alpha_f), ac[u].y, rc[u].y)) : rc[u]; \
+        if (use_ap) r[i0 + (long long)u * W] = v;                                                              \
+        prr = fmaf(v.x, v.x, fmaf(v.y, v.y, prr));                                                             \
+      }                                                                                                        \
+      rc[u] = v;                                                                                               \
+      sts64(sm.r + (sl0 + u * IC_PITCH) * 8, v);                                                               \
+    }                                                                                                          \
+    acc_rr += (double)prr;                                                                                     \
+    cp_async_wait_all();                                                                                       \
+    __syncwarp();                                                                                              \
+    if (!(P.debug & 1)) ic_sweeps(sm, ty, tx);                                                                 \
+    __syncwarp();                                                                                              \
+    _Pragma("unroll")                                                                                          \
+    for (int u = 0; u < 8; ++u) {                                                                              \
+      if (px < W && py0 + u < H) {                                                                             \
+        const float2 zz = lds64(sm.r + (sl0 + u * IC_PITCH) * 8);                                              \
+        z[i0 + (long long)u * W] = zz;                                                                         \
+        prz = fmaf(rc[u].x, zz.x, fmaf(rc[u].y, zz.y, prz));                                                   \
       }                                                                                                        \
     }                                                                                                          \
+    acc_rz += (double)prz;                                                                                     \
   }
 
   // ---------------- init ----------------
@@ -502,7 +484,6 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
             WHf[i] = fwh;
             WVf[i] = fwv;
             const uint2 wp = make_uint2(ic_pack(fwh.x, fwh.y), ic_pack(fwv.x, fwv.y));
-            Wpk[i] = wp;
             const double2 rb = __ldg(&S.rhs[i]);
             v = make_float2((float)rb.x, (float)rb.y);
             x[i] = make_double2(0.0, 0.0);
@@ -515,13 +496,11 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
           }
           sts64(sm.r + sl * 8, v); sts128(sm.c0 + sl * 16, c0); sts32(sm.cw + sl * 4, cw);
         }
-        ic_stage_sync();
-        if (ty < IC_SWEEP_WARPS) {
-          ic_factor(sm, ty, tx);
-          __syncwarp();
-          ic_sweeps(sm, ty, tx);
-        }
-        ic_stage_sync();
+        __syncwarp();
+        ic_factor(sm, ty, tx);
+        __syncwarp();
+        ic_sweeps(sm, ty, tx);
+        __syncwarp();
 #pragma unroll 2
         for (int u = 0; u < 8; ++u) {
           const int py = py0 + u;
@@ -529,9 +508,9 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
             const long long i = base + (long long)py * W + px;
             const int sl = ic_slot(ty * 8 + u, tx);
             const float2 zz = lds64(sm.r + sl * 8), rv = r[i];
-            const float4 c0 = lds128(sm.c0 + sl * 16);
             z[i] = zz;
-            Minv[i] = c0.x; Minv[n_all + i] = c0.y; Minv[2 * n_all + i] = c0.z;
+            C0[i] = lds128(sm.c0 + sl * 16);             // {i11, i12, i22, bf16x2 {wuh, wvh}}
+            CW[i] = lds32(sm.cw + sl * 4);               // bf16x2 {wuv, wvv}, 0 on every eighth row
             acc_rz += (double)rv.x * (double)zz.x + (double)rv.y * (double)zz.y;
           }
         }
