@@ -867,7 +867,11 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     MixParams P;
     P.sys = sys; P.w = w; P.x = x;
     P.tol2 = tol * tol;
-    P.delta2 = PCG_RELIABLE_DELTA * PCG_RELIABLE_DELTA;
+    {
+      const char *dl = getenv("B200FLOW_RELIABLE_DELTA");     // tuning override of the reliable-update threshold
+      const double delta = dl ? atof(dl) : (mode == PCG_MODE_MIXED_IC ? PCG_RELIABLE_DELTA_IC : PCG_RELIABLE_DELTA);
+      P.delta2 = delta * delta;
+    }
     P.maxit = maxit;
     P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.tiles_per_sys = tiles_per_sys;
     P.debug = 0;

@@ -3,21 +3,25 @@
 // Jacobi.  Replaces scipy.sparse.linalg.spsolve behind BaseOpticalFlow._solve_linear_system (base.py:87-114).
 //
 // Why: the solver is HBM-bound (solve.cu), so the only way to make a solve much faster is FEWER iterations, and the
-// preconditioner may spend any amount of on-chip work as long as it adds little HBM traffic.  IC(0) of the five-point
-// block stencil needs no fill-in storage: M = (P + L) P^-1 (P + L)^T with L the strictly lower part of A itself and
+// preconditioner may spend on-chip work freely as long as it adds little HBM traffic.  IC(0) of the five-point block
+// stencil needs no fill-in storage: M = (P + L) P^-1 (P + L)^T with L the strictly lower part of A itself and
 // P_i = A_ii - sum_{j in {left, up}} W_ij P_j^-1 W_ij (W_ij = diag(w_u, w_v) of the edge), so the preconditioner is
-// the 12 B/pixel P^-1 that block Jacobi already stores plus the edge weights the matvec reads anyway.  Couplings are
-// cut at the borders of 8-row x 32-column sub-tiles, which makes the two triangular solves local: a macro-tile of
-// 64 x 32 pixels (eight sub-tiles) is staged in shared memory and two warps sweep the eight sub-tiles along their
-// anti-diagonals (lane = row, 39 steps forward + 39 back, neighbours through warp shuffles, PUSH form so that both
-// sweeps use only the pixel's own coefficients).  scripts/ic_proto.py / ic32_proto.py (real Classic+NL systems):
-// 470 -> 211 iterations (alpha = 0), 60 -> 26 (alpha = 1), in fp32 exactly as done here.
+// the 12 B/pixel P^-1 that block Jacobi already stores plus a bf16 copy of the edge weights (8 B/pixel).  Couplings
+// are cut at the borders of 8 x 8 sub-tiles, which makes the two triangular solves local: every warp stages one STRIP
+// (8 rows x 32 columns = four sub-tiles) in shared memory and sweeps it along the anti-diagonals (lane = (sub-tile,
+// row), 15 steps forward + 15 back, neighbour rows through warp shuffles, PUSH form so that both sweeps use only the
+// pixel's own coefficients).  scripts/ic_proto.py / ic32_proto.py (real Classic+NL systems, fp32 factor, truncated
+// bf16 edges, exactly as here): 470 -> 231 iterations (alpha = 0), 60 -> 27 (alpha = 1); bench step 3015 -> 1485.
 //
 // Algorithmic bytes per pixel-iteration (fp32 working set):
 //   A  read z 8, p_old 8, y 8, D 8, a12 4, WH 8, WV 8; write p 8, y 8, Ap 8                              = 76
 //   B  read r 8, Ap 8, {P^-1 12, 4 edge weights as truncated bf16 8} by cp.async; write r 8, z 8          = 52
 //                                                                                            total        128 B
-// Everything else (all-system scalar tracking, re-dealing of the active tiles, reliable updates on the fp64 true
+// Measured per phase at 16 x 480 x 640 (IC_TIMERS build): A 66 us = 5.6 TB/s, B 44 us = 5.8 TB/s, two grid barriers +
+// scalar reductions 13 us.  The unit of work dealt to the CTAs is the strip (19 200 strips over 296 CTAs: < 1 %
+// imbalance); in phase A a strip is the CTA's 32 x 8 thread tile, in phase B the CTA's strips go round-robin to its
+// eight warps, which never synchronise with each other there.
+// Everything else (all-system scalar tracking, re-dealing of the active strips, reliable updates on the fp64 true
 // residual, determinism) is as in pcg_mixed_kernel.
 #include "solve_shared.cuh"
 
@@ -29,26 +33,18 @@ namespace bf {
 #define IC_THREADS 256                         // threads per CTA: 256 (2 CTAs / SM) or 128 (4 CTAs / SM)
 #endif
 constexpr int IC_TH = IC_THREADS / 32;         // rows of one 32 x IC_TH thread tile (phase A: one pixel per thread)
-constexpr int IC_NSTRIP = IC_THREADS / 32;     // strips (8 rows x 32 columns) per macro-tile: one per warp in phase B
+constexpr int IC_NSTRIP = IC_THREADS / 32;     // strips (8 rows x 32 columns) staged at a time: one per warp in phase B
 constexpr int IC_ROWS = IC_NSTRIP * 8;         // staged rows
 constexpr int IC_PITCH = 34;                   // staged row pitch in elements (see ic_slot)
 constexpr int IC_PAD = 8;                      // guard elements before / after each staged array (idle wavefront steps)
 constexpr int IC_NSLOT = IC_ROWS * IC_PITCH + 2 * IC_PAD;
-// Footprint of a macro-tile in the IMAGE: its strips are laid out IC_GX across, so that a macro-tile row is
-// IC_GX * 256 contiguous bytes of every float2 stream.  IC_GX = 1 is a vertical stack of strips.
-#ifndef IC_GX
-#define IC_GX 2
-#endif
-constexpr int IC_GY = IC_NSTRIP / IC_GX;
-constexpr int IC_MWPX = 32 * IC_GX, IC_MHPX = 8 * IC_GY;
-static_assert(IC_GX * IC_GY == IC_NSTRIP, "strips must tile the macro-tile");
+static_assert(IC_THREADS == 256, "phase A maps one 32 x 8 thread tile onto one strip");
 constexpr int IC_SW = 8;                       // sub-tile = 8 rows x 8 columns (scripts/ic32_proto.py: 231 iterations vs 470)
 constexpr int IC_STEPS = IC_SW + 8 - 1;        // anti-diagonals of one sub-tile
 #ifndef IC_SWEEP_UNROLL_N
 #define IC_SWEEP_UNROLL_N 5                     // of the 15 wavefront steps (a full unroll exhausts the 7 predicate registers)
 #endif
 constexpr int IC_SWEEP_UNROLL = IC_SWEEP_UNROLL_N;
-constexpr int IC_SUBS = 8;                     // 32 x IC_TH thread tiles per macro-tile
 // staged per pixel: float4 {i11, i12, i22, bf16x2 {wuh, wvh}} + bf16x2 {wuv, wvv} + float2 r = 28 B
 constexpr size_t IC_SMEM = (size_t)IC_NSLOT * (sizeof(float4) + sizeof(unsigned) + sizeof(float2));   // 60 KB at 256 threads
 
@@ -307,7 +303,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   const int H = S.H, W = S.W, B = S.B;
   const long long HW = (long long)H * W;
   const long long n_all = (long long)B * HW;
-  const int tps = P.tiles_per_sys;          // MACRO-tiles per system
+  const int tps = P.tiles_per_sys;          // strips (8 rows x 32 columns) per system
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int tid = threadIdx.x;
   int GW = 32;
@@ -344,7 +340,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   int *iters_g = P.w.flags + 1 + B;
   double *relres_g = P.w.scal;
 
-  // ---- macro-tile ownership: the macro-tiles of the unfinished systems, in compact order, are dealt to the CTAs in
+  // ---- strip ownership: the strips of the unfinished systems, in compact order, are dealt to the CTAs in
   //      contiguous chunks of s_tpc; recomputed (identically by every CTA) whenever a system finishes
 #define REMAP()                                                                         \
   {                                                                                     \
@@ -374,14 +370,13 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   const long long ta = tbase > t0 ? tbase : t0;                                                  \
   const long long tb = tbase + tps < t1 ? tbase + tps : t1;                                      \
   const long long base = (long long)b * HW;
-  // pixel of this thread in 32 x 8 thread tile v (v = macro-tile * 8 + sub-row-block) of the current system
+  // pixel of this thread in strip v of the current system (phase A: one pixel per thread, the strip is the 32 x 8 thread tile)
 #define PIXEL_OF(v, px, py, i, ok)                                                               \
   {                                                                                              \
-    int tl = (int)(((v) >> 3) - tbase);                                                          \
-    const int k_ = (int)((v) & 7) * IC_TH, st_ = k_ >> 3;        /* strip and row offset of sub-tile */ \
-    px = (tl % P.tiles_x) * IC_MWPX + (st_ % IC_GX) * 32 + tx;                                   \
-    py = (tl / P.tiles_x) * IC_MHPX + (st_ / IC_GX) * 8 + (k_ & 7) + ty;                         \
-    ok = (v) < tb * IC_SUBS && px < W && py < H;                                                 \
+    const int tl = (int)((v) - tbase);                                                           \
+    px = (tl % P.tiles_x) * 32 + tx;                                                             \
+    py = (tl / P.tiles_x) * 8 + ty;                                                              \
+    ok = (v) < tb && px < W && py < H;                                                           \
     i = ok ? base + (long long)py * W + px : base;                                               \
   }
 #define REDUCE_ALL(pa, pb, want)                                                        \
@@ -402,7 +397,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
     __syncthreads();                                                                    \
   }
 
-  // ---- phase B of one macro-tile: r -= alpha Ap (skipped when !use_ap), z = M^-1 r by the staged IC sweeps.  Thread
+  // ---- phase B of one strip: r -= alpha Ap (skipped when !use_ap), z = M^-1 r by the staged IC sweeps.  Thread
   //      (ty, tx) owns rows 0 .. 7 of column tx of strip ty; a warp stages, sweeps and writes back its strip on its own
   //      (warp barriers only), so the 16 warps of an SM overlap each other's loads and sweeps.  ONE round trip to
   //      memory per tile: the coefficients travel global -> shared asynchronously (cp.async, no registers) while
@@ -411,8 +406,8 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
 #define PHASE_B_TILE(t, alpha_f, use_ap, acc_rz, acc_rr)                                                       \
   {                                                                                                            \
     const int tl = (int)((t) - tbase);                                                                         \
-    const int px = (tl % P.tiles_x) * IC_MWPX + (ty % IC_GX) * 32 + tx;                                        \
-    const int py0 = (tl / P.tiles_x) * IC_MHPX + (ty / IC_GX) * 8;                                             \
+    const int px = (tl % P.tiles_x) * 32 + tx;                                                                 \
+    const int py0 = (tl / P.tiles_x) * 8;                                                                      \
     const long long i0 = base + (long long)py0 * W + px;                                                       \
     const int sl0 = ic_slot(ty * 8, tx);                                                                       \
     float2 rc[8], ac[8];                                                                                       \
@@ -462,10 +457,10 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
     for (int a = a_first; a <= a_last; ++a) {
       TILE_RANGE(a)
       double acc_rz = 0.0, acc_bb = 0.0;
-      for (long long t = ta; t < tb; ++t) {
+      for (long long t = ta + ty; t < tb; t += IC_NSTRIP) {     // strips of this CTA, dealt round-robin to its warps
         const int tl = (int)(t - tbase);
-        const int px = (tl % P.tiles_x) * IC_MWPX + (ty % IC_GX) * 32 + tx;
-        const int py0 = (tl / P.tiles_x) * IC_MHPX + (ty / IC_GX) * 8;
+        const int px = (tl % P.tiles_x) * 32 + tx;
+        const int py0 = (tl / P.tiles_x) * 8;
 #pragma unroll 2
         for (int u = 0; u < 8; ++u) {
           const int py = py0 + u;
@@ -552,7 +547,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
       const double aprev_d = s_alpha[b];
       const bool flush = s_flush[b] != 0;       // a reliable update happened: fold y + alpha p into the fp64 solution now
       double acc = 0.0, dummy = 0.0;
-      for (long long v = ta * IC_SUBS; v < tb * IC_SUBS; v += IC_UA) {
+      for (long long v = ta; v < tb; v += IC_UA) {
         int px[IC_UA], py[IC_UA]; long long i[IC_UA]; bool ok[IC_UA];
         float2 zc[IC_UA], po[IC_UA], zl[IC_UA], pl[IC_UA], zr[IC_UA], pr[IC_UA], zu[IC_UA], pu[IC_UA], zd[IC_UA],
             pd[IC_UA], sd[IC_UA], swr[IC_UA], swd[IC_UA], swl[IC_UA], swu[IC_UA], yc[IC_UA];
@@ -620,7 +615,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
       TILE_RANGE(a)
       const float alpha = (float)s_alpha[b];
       double acc_rz = 0.0, acc_rr = 0.0;
-      for (long long t = ta; t < tb; ++t) PHASE_B_TILE(t, alpha, true, acc_rz, acc_rr)
+      for (long long t = ta + ty; t < tb; t += IC_NSTRIP) PHASE_B_TILE(t, alpha, true, acc_rz, acc_rr)
       ic_block_sum2(acc_rz, acc_rr, sm_red);
       if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
     }
@@ -648,7 +643,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
         if (s_state[b] != 3) continue;
         const double alpha = s_alpha[b];
         double acc_rz = 0.0, acc_rr = 0.0, acc_dummy = 0.0;
-        for (long long v = ta * IC_SUBS; v < tb * IC_SUBS; ++v) {
+        for (long long v = ta; v < tb; ++v) {
           int px, py; long long i; bool ok;
           PIXEL_OF(v, px, py, i, ok)
           if (!ok) continue;
@@ -656,8 +651,8 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
           r[i] = make_float2((float)rt.x, (float)rt.y);
           acc_rr += rt.x * rt.x + rt.y * rt.y;
         }
-        __syncthreads();                       // r of the own macro-tiles is complete (same ownership in both passes)
-        for (long long t = ta; t < tb; ++t) PHASE_B_TILE(t, 0.f, false, acc_rz, acc_dummy)
+        __syncthreads();                       // r of the own strips is complete (same ownership in both passes)
+        for (long long t = ta + ty; t < tb; t += IC_NSTRIP) PHASE_B_TILE(t, 0.f, false, acc_rz, acc_dummy)
         ic_block_sum2(acc_rz, acc_rr, sm_red);
         if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
       }
@@ -690,7 +685,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
           TILE_RANGE(a)
           if (s_state[b] != 2) continue;
           const double alpha = s_alpha[b];
-          for (long long v = ta * IC_SUBS; v < tb * IC_SUBS; ++v) {
+          for (long long v = ta; v < tb; ++v) {
             int px, py; long long i; bool ok;
             PIXEL_OF(v, px, py, i, ok)
             if (!ok) continue;
@@ -748,8 +743,8 @@ int k_pcg_ic_launch(b200flow_ctx *ctx, MixParams P, int grid_max) {
   const LinSys &sys = P.sys;
   if (sys.B > MAXB)
     return set_err(ctx, B200FLOW_EINVAL, "batch of %d systems exceeds %d per solve; split the batch", sys.B, MAXB);
-  P.tiles_x = (int)cdiv(sys.W, IC_MWPX);
-  P.tiles_y = (int)cdiv(sys.H, IC_MHPX);
+  P.tiles_x = (int)cdiv(sys.W, 32);      // strips of 8 rows x 32 columns: the unit that is dealt to the CTAs
+  P.tiles_y = (int)cdiv(sys.H, 8);
   P.tiles_per_sys = P.tiles_x * P.tiles_y;
   const long long total = (long long)P.tiles_per_sys * sys.B;
   int G = grid_max;

@@ -16,6 +16,6 @@ cap rof_iter rof_iter 300
 cap level_prep level_prep 13
 cap gauss_resize gauss_resize 20
 cap clip_add clip_add 41
-timeout 300 ncu --set full --clock-control none --import-source on --kernel-name pcg_mixed_kernel --launch-skip 41 --launch-count 1 \
-    -o $O/${R}_pcg_mixed -f python scripts/trace_step.py 16 mixed > $O/${R}_full_pcg.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on --kernel-name pcg_ic_kernel --launch-skip 41 --launch-count 1 \
+    -o $O/${R}_pcg_ic -f python scripts/trace_step.py 16 mixed > $O/${R}_full_pcg.log 2>&1
 ls -la $O | grep ${R}_ | tail -20
