@@ -98,6 +98,11 @@ int  b200flow_ctx_set_timing(b200flow_ctx *ctx, int enabled);   /* per-stage CUD
 int  b200flow_ctx_sync(b200flow_ctx *ctx);
 void *b200flow_ctx_stream(b200flow_ctx *ctx);               /* the cudaStream_t, for torch / event interop */
 int  b200flow_ctx_num_sms(const b200flow_ctx *ctx);
+/* page-locked host memory for the caller's result buffers: a device->host copy into pageable memory is staged and
+ * page-faults on first touch (15 ms for a 16-pair 640x480 flow stack), into pinned memory it is one DMA (2 ms).  The
+ * Python drop-in (optical_flow/_lib.py: pinned_empty) hands such buffers out as NumPy arrays and recycles them. */
+int  b200flow_host_alloc(b200flow_ctx *ctx, unsigned long long bytes, void **out);
+int  b200flow_host_free(b200flow_ctx *ctx, void *ptr);
 
 /* ---- whole pipeline: replaces {HS,BA,ClassicNL}OpticalFlow.compute_flow (hs.py:49-99, ba.py:57-138,
  *      classic_nl.py:89-198) for a batch of B same-size pairs.

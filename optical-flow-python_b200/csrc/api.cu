@@ -89,6 +89,20 @@ int b200flow_ctx_sync(b200flow_ctx *ctx) {
 void *b200flow_ctx_stream(b200flow_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int b200flow_ctx_num_sms(const b200flow_ctx *ctx) { return ctx ? ctx->num_sms : 0; }
 
+int b200flow_host_alloc(b200flow_ctx *ctx, unsigned long long bytes, void **out) {
+  if (!ctx || !out) return B200FLOW_EINVAL;
+  *out = nullptr;
+  BF_CUDA(ctx, cudaSetDevice(ctx->device));
+  BF_CUDA(ctx, cudaHostAlloc(out, bytes ? (size_t)bytes : 1, cudaHostAllocPortable));
+  return 0;
+}
+
+int b200flow_host_free(b200flow_ctx *ctx, void *ptr) {
+  if (!ctx) return B200FLOW_EINVAL;
+  if (ptr) BF_CUDA(ctx, cudaFreeHost(ptr));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // whole pipeline
 // ------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@ if the shared library is missing, or no sm_100 (B200) GPU is usable, every opera
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -85,6 +86,9 @@ _SIGS = {
     "b200flow_flow_to_flo": [_vp, C.c_int, C.c_int, C.c_int, _vp],
     "b200flow_debug_pcg_bench": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp],
 }
+_SIGS["b200flow_host_alloc"] = [C.c_ulonglong, C.POINTER(_vp)]
+_SIGS["b200flow_host_free"] = [_vp]
+
 EXPORTS = sorted(list(_SIGS) + ["b200flow_abi_version", "b200flow_ctx_create", "b200flow_ctx_destroy",
                                 "b200flow_last_error", "b200flow_ctx_set_timing", "b200flow_ctx_sync",
                                 "b200flow_ctx_stream", "b200flow_ctx_num_sms"])
@@ -138,6 +142,9 @@ class Context:
 
     def close(self):
         if getattr(self, "handle", None):
+            for free in self.__dict__.get("_pinned_free", {}).values():     # buffers still owned by live arrays stay valid
+                while free:
+                    self.lib.b200flow_host_free(self.handle, _vp(free.pop()))
             self.lib.b200flow_ctx_destroy(self.handle)
             self.handle = None
 
@@ -172,6 +179,26 @@ class Context:
     @property
     def num_sms(self):
         return self.lib.b200flow_ctx_num_sms(self.handle)
+
+    # ---- page-locked result buffers ---------------------------------------------------------------------------
+    def pinned_empty(self, shape, dtype=np.float64):
+        """Uninitialised C-contiguous NumPy array in page-locked host memory (cudaHostAlloc), so that the device->host
+        copy of a result is one DMA instead of a staged copy into freshly mapped pageable pages.  The memory goes back to
+        a per-context free list when the array (and every view of it) is garbage collected and is handed out again for
+        the next request of the same size: a loop of `uv = estimate_flow_batch(...)` allocates twice and then recycles."""
+        shape = tuple(int(v) for v in np.atleast_1d(shape))
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        pool = self.__dict__.setdefault("_pinned_free", {})
+        free = pool.setdefault(nbytes, [])
+        if free:
+            addr = free.pop()
+        else:
+            p = _vp()
+            self.call("b200flow_host_alloc", C.c_ulonglong(max(nbytes, 1)), C.byref(p))
+            addr = p.value
+        buf = (C.c_char * max(nbytes, 1)).from_address(addr)
+        weakref.finalize(buf, free.append, addr)          # recycled, not freed: pinning 80 MB costs ~10 ms
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 _tls = threading.local()

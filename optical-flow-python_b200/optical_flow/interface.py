@@ -73,9 +73,9 @@ def estimate_flow_batch(ims1, ims2, method='classic+nl-fast', params=None, devic
     if ope.pyramid_levels < 1:
         P.pyramid_levels, P.auto_level = 0, 1
     ope._apply_solver(P)
-    uv = np.empty((B, H, W, 2))
     st = _lib.Stats()
     ctx = _lib.default_context(device)
+    uv = ctx.pinned_empty((B, H, W, 2))       # page-locked: the result comes back in one DMA
     ctx.call("b200flow_estimate_rgb8", P, B, H, W, _lib.ptr(ims1), _lib.ptr(ims2), int(ope.color_images is not None),
              _lib.ptr(uv), _lib.C.byref(st))
     return (uv, st.as_dict()) if return_stats else uv

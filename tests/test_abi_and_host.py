@@ -164,3 +164,39 @@ def test_shard_indices():
     from optical_flow.interface import shard_indices
     parts = [shard_indices(10, r, 4) for r in range(4)]
     assert sorted(sum(parts, [])) == list(range(10)) and parts[1] == [1, 5, 9]
+
+
+def test_pinned_result_buffers_are_recycled_only_when_released():
+    """Context.pinned_empty (result buffers of estimate_flow_batch): a buffer goes back to the free list only when the
+    array AND every view of it are gone; the allocator itself is faked here (no GPU)."""
+    import ctypes as C
+    import gc
+    from optical_flow import _lib
+
+    class Fake(_lib.Context):
+        def __init__(self):
+            self.n, self.keep = 0, []
+
+        def call(self, name, nbytes, pref):
+            assert name == "b200flow_host_alloc"
+            self.n += 1
+            b = C.create_string_buffer(nbytes.value)
+            self.keep.append(b)
+            C.cast(pref, C.POINTER(C.c_void_p))[0] = C.addressof(b)
+
+        def __del__(self):
+            pass
+
+    f = Fake()
+    a = f.pinned_empty((4, 5, 2))
+    assert a.shape == (4, 5, 2) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"]
+    a[:] = 1.5
+    view, addr = a[1:], a.ctypes.data
+    del a
+    gc.collect()
+    b = f.pinned_empty((4, 5, 2))                 # the view is alive: a NEW buffer
+    assert b.ctypes.data != addr and f.n == 2 and float(view[0, 0, 0]) == 1.5
+    del view
+    gc.collect()
+    c = f.pinned_empty((4, 5, 2))                 # released: recycled, no new allocation
+    assert c.ctypes.data == addr and f.n == 2
