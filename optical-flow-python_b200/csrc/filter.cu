@@ -287,20 +287,45 @@ __device__ __forceinline__ void acc_le(double x, double p, double w, double &s, 
       : "+d"(s), "+r"(c) : "d"(x), "d"(p), "d"(w));
 }
 
+// exact S(p) = sum of the weights of the samples <= p, fp64 (all lanes return it)
+template <int NPL>
+__device__ __forceinline__ double exact_cum_weight(const double (&x)[NPL], const double (&w)[NPL], double p) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < NPL; ++k) s += x[k] <= p ? w[k] : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// Fixed-point shadow of the weights for the bracketing phase: pk = (floor(w * 2^22 / total) << 9) | 1.  One predicated
+// integer add per sample accumulates BOTH the weight below the pivot (high 23 bits; the sum over a window is <= 2^22)
+// and the number of samples below it (low 9 bits, <= 256), and ONE REDUX.SUM reduces both over the warp -- against
+// DSETP + DADD + 2 FSEL + IADD per sample and 25 instructions of fp64 shuffle tree.  Truncation loses < 1 unit per
+// sample, so with F = the reduced high field and c = the count the true S(p) * 2^22 / total lies in [F, F + c]: the
+// comparison with total / 2 (= 2^21) is decided in fixed point whenever it is safe by a margin, and falls back to the
+// exact fp64 sum otherwise (ties and near-ties only).
+constexpr unsigned WM_HALF_FIX = 1u << 21;
+__device__ __forceinline__ unsigned wm_pack(double w, double scale) {
+  return (__double2uint_rz(w * scale) << 9) | 1u;
+}
+
 // Weighted median of the n samples x[] with weights w[] held NPL per lane in the warp's registers (all lanes return it):
 //   t* = min { x_k : S(x_k) >= half },  S(t) = sum of w_k over x_k <= t.
-// Padding slots hold x = +inf, w = 0, so they are never counted, weighed or bracketed.
-// Stage 1 bisects the VALUE range (L, R] -- invariant S(L) < half <= S(R) -- with steps that only need S(p) and the
-//   count n(p) (one fp64 shuffle reduction + one integer REDUX); a step that separates nothing (ties / clusters) snaps
-//   the bracket to the extreme samples inside it.
-// Stage 2, as soon as at most 32 samples are left inside the bracket (about 4 steps for 225 samples), compacts them one
+// Padding slots hold x = +inf, w = 0, pk = 0, so they are never counted, weighed or bracketed.
+// Stage 1 bisects the VALUE range (L, R] -- invariant S(L) < half <= S(R) -- with steps that only need to know on which
+//   side of half S(p) lies and the count n(p): the fixed-point shadow above (pk), exact fp64 only when that is not
+//   decisive; a step that separates nothing (ties / clusters) snaps the bracket to the extreme samples inside it.
+//   S(L) itself is evaluated once, exactly, when the bracket is final.
+// Stage 2, as soon as at most 32 samples are left inside the bracket (about 4-5 steps for 225 samples), compacts them one
 //   per lane through `scratch` (warp-private shared memory).
 // Stage 3 keeps bisecting on that one-sample-per-lane set (a step is now ~25 instructions) down to <= 8 survivors and
 //   finishes exactly: every survivor evaluates S at its own value (S(L) + an all-pairs pass over the survivors) and
 //   the smallest one with S >= half is the answer.  The result is always one of the window's samples.
 template <int NPL>
-__device__ __forceinline__ double weighted_select(const double (&x)[NPL], const double (&w)[NPL], int n, double half,
-                                                  double2 *scratch, int lane) {
+__device__ __forceinline__ double weighted_select(const double (&x)[NPL], const double (&w)[NPL],
+                                                  const unsigned (&pk)[NPL], int n, double half, double2 *scratch,
+                                                  int lane) {
   // value range in fp32 with outward rounding (FMNMX instead of fp64 compare + select pairs)
   float flo = __double2float_rd(x[0]), fhi = -INFINITY;
 #pragma unroll
@@ -315,21 +340,23 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
     fhi = fmaxf(fhi, __shfl_xor_sync(0xffffffffu, fhi, o));
   }
   double L = next_below((double)flo), R = (double)fhi;   // open-closed value bracket: S(L) = 0 < half <= S(R) = total
-  double SL = 0.0;                                       // S(L)
   int nL = 0, nR = n;                                    // samples <= L, <= R
   while (nR - nL > 32) {
     double p = 0.5 * (L + R);
     bool snap = !(p > L && p < R);
     if (!snap) {
-      double s = 0.0;
-      int c = 0;
+      unsigned acc = 0u;
 #pragma unroll
-      for (int k = 0; k < NPL; ++k) acc_le(x[k], p, w[k], s, c);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (s >= half) { snap = c == nR; R = p; nR = c; }
-      else { snap = c == nL; L = p; nL = c; SL = s; }
+      for (int k = 0; k < NPL; ++k) acc += x[k] <= p ? pk[k] : 0u;
+      acc = __reduce_add_sync(0xffffffffu, acc);
+      const int c = (int)(acc & 511u);
+      const unsigned f = acc >> 9;
+      bool ge;                                             // S(p) >= half ?
+      if (f >= WM_HALF_FIX + 4u) ge = true;
+      else if (f + (unsigned)c + 4u < WM_HALF_FIX) ge = false;
+      else ge = exact_cum_weight<NPL>(x, w, p) >= half;    // too close to call in fixed point
+      if (ge) { snap = c == nR; R = p; nR = c; }
+      else { snap = c == nL; L = p; nL = c; }
     }
     if (snap) {
       // a = smallest sample > L, b = largest sample <= R  (both exist: the bracket holds weight)
@@ -349,6 +376,7 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
       L = next_below(a); R = b;            // no sample lies in (old L, new L]: S(L) and the counts are unchanged
     }
   }
+  double SL = nL > 0 ? exact_cum_weight<NPL>(x, w, L) : 0.0;   // S(L), exactly, for the final evaluation
   // stage 2: compact the survivors (L < x <= R), one per lane
   int cnt = 0;
   const unsigned lt = (1u << lane) - 1u;
@@ -456,13 +484,19 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     const double half = tot / 2.0;
+    unsigned pk[NPL];
+    {
+      const double scale = 4194304.0 / tot;                  // 2^22 / total
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) pk[k] = ((vmask >> k) & 1u) ? wm_pack(w[k], scale) : 0u;
+    }
     // padding slots: x = +inf with zero weight (never counted, weighed or bracketed)
 #pragma unroll
     for (int k = 0; k < NPL; ++k) x[k] = ((vmask >> k) & 1u) ? s_uv[org + qoff[k]].x : INFINITY;
-    const double mu = weighted_select<NPL>(x, w, n, half, s_scr, lane);
+    const double mu = weighted_select<NPL>(x, w, pk, n, half, s_scr, lane);
 #pragma unroll
     for (int k = 0; k < NPL; ++k) x[k] = ((vmask >> k) & 1u) ? s_uv[org + qoff[k]].y : INFINITY;
-    const double mv = weighted_select<NPL>(x, w, n, half, s_scr, lane);
+    const double mv = weighted_select<NPL>(x, w, pk, n, half, s_scr, lane);
     if (lane == 0) {
       long long gi = off + (long long)py * W + px;
       if (base) {
