@@ -39,10 +39,14 @@ constexpr int IC_PITCH = 34;                   // staged row pitch in elements (
 constexpr int IC_PAD = 8;                      // guard elements before / after each staged array (idle wavefront steps)
 constexpr int IC_NSLOT = IC_ROWS * IC_PITCH + 2 * IC_PAD;
 static_assert(IC_THREADS == 256, "phase A maps one 32 x 8 thread tile onto one strip");
-constexpr int IC_SW = 8;                       // sub-tile = 8 rows x 8 columns (scripts/ic32_proto.py: 231 iterations vs 470)
-constexpr int IC_STEPS = IC_SW + 8 - 1;        // anti-diagonals of one sub-tile
+#ifndef IC_SW
+#define IC_SW 8                                // sub-tile = 8 rows x IC_SW columns, 8 or 16 (scripts/ic32_proto.py: 231 / 212 iterations vs 470)
+#endif
+static_assert(IC_SW == 8 || IC_SW == 16, "sub-tile width");
+// anti-diagonals of one sub-tile (IC_SW + 7), rounded up to a multiple of the unroll factor: a surplus step is idle for every lane
+constexpr int IC_STEPS = IC_SW == 8 ? 15 : 24;
 #ifndef IC_SWEEP_UNROLL_N
-#define IC_SWEEP_UNROLL_N 5                     // of the 15 wavefront steps (a full unroll exhausts the 7 predicate registers)
+#define IC_SWEEP_UNROLL_N (IC_SW == 8 ? 5 : 6)  // of the wavefront steps (a full unroll exhausts the 7 predicate registers)
 #endif
 constexpr int IC_SWEEP_UNROLL = IC_SWEEP_UNROLL_N;
 // staged per pixel: float4 {i11, i12, i22, bf16x2 {wuh, wvh}} + bf16x2 {wuv, wvv} + float2 r = 28 B
@@ -158,11 +162,12 @@ struct IcSmem {            // shared-space byte addresses of the three staged ar
 //  * guard slots and the two pad columns are zeroed once per kernel, so idle-step garbage is always finite.
 __device__ __forceinline__ void ic_sweeps(const IcSmem sm, int w, int lane) {
   const unsigned full = 0xffffffffu;
-  const int q = lane >> 3, j = lane & 7;
+  // with 16-wide sub-tiles a strip holds two of them: lanes 16..31 repeat the work (and the identical stores) of lanes 0..15
+  const int q = IC_SW == 8 ? lane >> 3 : (lane >> 3) & 1, j = lane & 7;
   const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
-  const int slot0 = ic_slot(8 * w + j, 8 * q - j);       // slot of step 0 (column -j); step s is slot0 + s
+  const int slot0 = ic_slot(8 * w + j, IC_SW * q - j);   // slot of step 0 (column -j); step s is slot0 + s
   const unsigned a0 = sm.c0 + slot0 * 16, ar = sm.r + slot0 * 8, aw = sm.cw + slot0 * 4;
-  const unsigned actmask = 0xffu << j;                   // bit s set: step s is inside the sub-tile
+  const unsigned actmask = ((1u << IC_SW) - 1u) << j;    // bit s set: step s is inside the sub-tile
   const unsigned keep = j == 7 ? 0u : 0xffffffffu;       // last row of a sub-tile never pushes down / pulls up
   {
     float cu = 0.f, cv = 0.f, pu = 0.f, pv = 0.f;        // pushed from the left (own row) / pushed down to the next row
@@ -221,9 +226,9 @@ __device__ __forceinline__ void ic_sweeps(const IcSmem sm, int w, int lane) {
 // runs once per solve, so it keeps a rolled loop and explicit masking.
 __device__ __forceinline__ void ic_factor(const IcSmem sm, int w, int lane) {
   const unsigned full = 0xffffffffu;
-  const int q = lane >> 3, j = lane & 7;
+  const int q = IC_SW == 8 ? lane >> 3 : (lane >> 3) & 1, j = lane & 7;
   const int up_lane = (lane + 31) & 31;
-  const int slot0 = ic_slot(8 * w + j, 8 * q - j);
+  const int slot0 = ic_slot(8 * w + j, IC_SW * q - j);
   float c11 = 0.f, c12 = 0.f, c22 = 0.f, p11 = 0.f, p12 = 0.f, p22 = 0.f;
 #pragma unroll 1
   for (int s = 0; s < IC_STEPS; ++s) {
