@@ -32,7 +32,6 @@ namespace bf {
 #ifndef IC_THREADS
 #define IC_THREADS 256                         // threads per CTA: 256 (2 CTAs / SM) or 128 (4 CTAs / SM)
 #endif
-constexpr int IC_TH = IC_THREADS / 32;         // rows of one 32 x IC_TH thread tile (phase A: one pixel per thread)
 constexpr int IC_NSTRIP = IC_THREADS / 32;     // strips (8 rows x 32 columns) staged at a time: one per warp in phase B
 constexpr int IC_ROWS = IC_NSTRIP * 8;         // staged rows
 constexpr int IC_PITCH = 34;                   // staged row pitch in elements (see ic_slot)

@@ -107,6 +107,60 @@ def test_pcg_determinism_and_batch(systems, precision):
     np.testing.assert_array_equal(x1, x2)
 
 
+@pytest.mark.parametrize("precision", ["mixed", "mixed-jacobi", "fp64"])
+def test_exact_solver_iteration_cap(systems, precision):
+    """exact_maxiter too small: the solve stops at the cap, reports it (iterations, residual above tol) and still
+    returns the finite iterate it reached -- no hang, no exception from the persistent kernel."""
+    from optical_flow import load_of_method
+    ope = load_of_method("classic+nl")
+    ope.solver_precision = precision
+    ope.exact_maxiter = 5
+    uv = systems["uv"]
+    A, b, _, _ = ope.flow_operator(uv, np.zeros_like(uv), systems["cnl_It"], systems["cnl_Ix"], systems["cnl_Iy"])
+    x = ope._solve_linear_system(A, b, uv.shape)
+    assert np.isfinite(x).all()
+    assert ope.last_stats["pcg_iters"] == 5 and ope.last_stats["relres"] > 1e-10
+    true_rel = float(np.linalg.norm(b - A @ _f(x)) / np.linalg.norm(b))
+    assert abs(true_rel - ope.last_stats["relres"]) <= 0.05 * true_rel + 1e-12     # the reported residual is the TRUE one
+    assert true_rel < 1.0
+
+
+def test_ic_preconditioner_halves_the_iterations(systems):
+    """The tile-local block-IC(0) preconditioner of the default solver against block Jacobi on the same systems (alpha = 0:
+    generalized Charbonnier weights spanning decades; alpha = 1: quadratic): same solution, at most 60 % of the iterations."""
+    from optical_flow import load_of_method
+    uv = systems["uv"]
+    for alpha in (0.0, 1.0):
+        its, xs = {}, {}
+        for prec in ("mixed", "mixed-jacobi"):
+            ope = load_of_method("classic+nl")
+            ope.solver_precision = prec
+            A, b = _blend(ope, alpha, uv, np.zeros_like(uv), systems["cnl_It"], systems["cnl_Ix"], systems["cnl_Iy"])
+            xs[prec] = ope._solve_linear_system(A, b, uv.shape)
+            its[prec] = ope.last_stats["pcg_iters"]
+        assert_close(xs["mixed"], xs["mixed-jacobi"], 2e-6, "IC vs Jacobi solution, alpha=%g" % alpha)
+        assert its["mixed"] <= 0.6 * its["mixed-jacobi"], its
+
+
+@pytest.mark.parametrize("precision", ["mixed", "mixed-jacobi", "fp64"])
+def test_zero_motion_gives_zero_increment(precision):
+    """Identical frames: It is rounding noise (1e-13), so the right-hand side is ~0: the solvers must return the ~0
+    increment (measured 5e-15 px) without dividing 0 by 0 in their scalar updates."""
+    from optical_flow import load_of_method
+    from optical_flow.utils.derivatives import partial_deriv
+    rng = np.random.default_rng(5)
+    im = rng.random((45, 70)) * 255
+    images = np.stack([im, im], axis=2)
+    ope = load_of_method("ba")
+    ope.solver_precision = precision
+    ope.images = images
+    uv = np.zeros((45, 70, 2))
+    It, Ix, Iy = partial_deriv(images, uv, ope.interpolation_method, ope.deriv_filter, 0.5)
+    A, b, _, _ = ope.flow_operator(uv, np.zeros_like(uv), It, Ix, Iy)
+    x = ope._solve_linear_system(A, b, uv.shape)
+    assert np.isfinite(x).all() and np.abs(x).max() < 1e-12
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the reference's own approximate solver modes (SURVEY 8f row 2)
 # ---------------------------------------------------------------------------------------------------------------
