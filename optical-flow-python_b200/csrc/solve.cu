@@ -868,8 +868,10 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     P.sys = sys; P.w = w; P.x = x;
     P.tol2 = tol * tol;
     {
-      const char *dl = getenv("B200FLOW_RELIABLE_DELTA");     // tuning override of the reliable-update threshold
-      const double delta = dl ? atof(dl) : (mode == PCG_MODE_MIXED_IC ? PCG_RELIABLE_DELTA_IC : PCG_RELIABLE_DELTA);
+      double delta = mode == PCG_MODE_MIXED_IC ? PCG_RELIABLE_DELTA_IC : PCG_RELIABLE_DELTA;
+#ifdef B200FLOW_TUNING                                        // tuning builds only (scripts/build_variant.sh ... -DB200FLOW_TUNING)
+      if (const char *dl = getenv("B200FLOW_RELIABLE_DELTA")) delta = atof(dl);
+#endif
       P.delta2 = delta * delta;
     }
     P.maxit = maxit;
@@ -887,13 +889,15 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
       BF_TRY(k_pcg_ic_launch(ctx, P, w.grid_ic));
     } else {
       void *args[] = {&P};
-      const char *dbg = getenv("B200FLOW_MIX_SMEM");          // tuning experiment: shrink L1 like the IC kernel's carve-out does
-      const int dyn = dbg ? atoi(dbg) : 0;
+      int dyn = 0;
+#ifdef B200FLOW_TUNING   // experiment behind profiles/r01_summary.md "L1 matters for phase A": shrink L1 with an unused dynamic carve-out
+      if (const char *dbg = getenv("B200FLOW_MIX_SMEM")) dyn = atoi(dbg);
       if (dyn > 0) {
         cudaFuncSetAttribute(pcg_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         const char *cv = getenv("B200FLOW_MIX_CARVEOUT");
         cudaFuncSetAttribute(pcg_mixed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
       }
+#endif
       BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_mixed_kernel, dim3(G), dim3(PCG_THREADS), args, dyn, ctx->stream));
     }
   } else {

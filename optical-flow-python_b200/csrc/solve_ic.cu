@@ -48,6 +48,11 @@ constexpr int IC_STEPS = IC_SW == 8 ? 15 : 24;
 #define IC_SWEEP_UNROLL_N (IC_SW == 8 ? 5 : 6)  // of the wavefront steps (a full unroll exhausts the 7 predicate registers)
 #endif
 constexpr int IC_SWEEP_UNROLL = IC_SWEEP_UNROLL_N;
+#ifdef B200FLOW_TUNING
+constexpr bool IC_TUNING = true;
+#else
+constexpr bool IC_TUNING = false;
+#endif
 // staged per pixel: float4 {i11, i12, i22, bf16x2 {wuh, wvh}} + bf16x2 {wuv, wvv} + float2 r = 28 B
 constexpr size_t IC_SMEM = (size_t)IC_NSLOT * (sizeof(float4) + sizeof(unsigned) + sizeof(float2));   // 60 KB at 256 threads
 
@@ -440,7 +445,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
     acc_rr += (double)prr;                                                                                     \
     cp_async_wait_all();                                                                                       \
     __syncwarp();                                                                                              \
-    if (!(P.debug & 1)) ic_sweeps(sm, ty, tx);                                                                 \
+    if (!(IC_TUNING && (P.debug & 1))) ic_sweeps(sm, ty, tx);                                                  \
     __syncwarp();                                                                                              \
     _Pragma("unroll")                                                                                          \
     for (int u = 0; u < 8; ++u) {                                                                              \
@@ -731,9 +736,11 @@ int pcg_ic_grid(b200flow_ctx *ctx, int *grid_out) {
   if (cached_dev != ctx->device) {
     int nb = 0;
     BF_CUDA(ctx, cudaFuncSetAttribute(pcg_ic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IC_SMEM));
-    const char *cv = getenv("B200FLOW_IC_CARVEOUT");
-    BF_CUDA(ctx, cudaFuncSetAttribute(pcg_ic_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cv ? atoi(cv) : IC_CARVEOUT_PCT));
+    int carve = IC_CARVEOUT_PCT;
+#ifdef B200FLOW_TUNING
+    if (const char *cv = getenv("B200FLOW_IC_CARVEOUT")) carve = atoi(cv);
+#endif
+    BF_CUDA(ctx, cudaFuncSetAttribute(pcg_ic_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     BF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcg_ic_kernel, IC_THREADS, IC_SMEM));
     if (nb < 1) return set_err(ctx, B200FLOW_ECUDA, "pcg_ic_kernel cannot be made resident");
     cached = nb * ctx->num_sms;
@@ -755,8 +762,10 @@ int k_pcg_ic_launch(b200flow_ctx *ctx, MixParams P, int grid_max) {
   if ((long long)G > total) G = (int)total;
   if (G < 1) G = 1;
   P.w.grid = G;
-  const char *dbg = getenv("B200FLOW_IC_DEBUG");
-  P.debug = dbg ? atoi(dbg) : 0;
+  P.debug = 0;
+#ifdef B200FLOW_TUNING                     // bit 0: skip the sweeps (z = staged r): what do they cost?
+  if (const char *dbg = getenv("B200FLOW_IC_DEBUG")) P.debug = atoi(dbg);
+#endif
   void *args[] = {&P};
   BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_ic_kernel, dim3(G), dim3(IC_THREADS), args, IC_SMEM, ctx->stream));
   return 0;

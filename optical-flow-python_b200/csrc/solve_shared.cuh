@@ -87,7 +87,7 @@ struct MixParams {
   double tol2, delta2;
   int maxit;
   int tiles_x, tiles_y, tiles_per_sys;
-  int debug;                     // B200FLOW_IC_DEBUG (tuning experiments only; 0 on the product path)
+  int debug;                     // tuning builds (-DB200FLOW_TUNING) only; always 0 on the product path
 };
 
 // solve_ic.cu
