@@ -197,7 +197,19 @@ def run_reference_arm(args, rank, world):
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
+_stdout_fd = None
+
+
+def _emit(line):
+    """rank 0's ONE JSON line, on the real stdout"""
+    sys.stdout.flush()
+    if _stdout_fd is not None:
+        os.dup2(_stdout_fd, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    global _stdout_fd
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -227,8 +239,10 @@ def main():
     os.environ["B200FLOW_DEVICE"] = str(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL prints its version banner on C-level stdout at the first collective: park fd 1 on stderr until the JSON line
+        sys.stdout.flush()
+        _stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W_ = max(3, args.warmup)
     B = args.batch
@@ -368,7 +382,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
