@@ -280,13 +280,6 @@ __device__ __forceinline__ double next_below(double x) {
   return -4.9406564584124654e-324;
 }
 
-// if (x <= p) { s += w; c += 1; }  as DSETP + predicated DADD + predicated IADD (the compiler's own rendering is
-// DSETP + DADD + 2 FSEL + SEL + IADD)
-__device__ __forceinline__ void acc_le(double x, double p, double w, double &s, int &c) {
-  asm("{\n\t.reg .pred q;\n\tsetp.le.f64 q, %2, %3;\n\t@q add.f64 %0, %0, %4;\n\t@q add.s32 %1, %1, 1;\n\t}"
-      : "+d"(s), "+r"(c) : "d"(x), "d"(p), "d"(w));
-}
-
 // exact S(p) = sum of the weights of the samples <= p, fp64 (all lanes return it)
 template <int NPL>
 __device__ __forceinline__ double exact_cum_weight(const double (&x)[NPL], const double (&w)[NPL], double p) {
