@@ -30,7 +30,7 @@ namespace cg = cooperative_groups;
 namespace bf {
 
 #ifndef IC_THREADS
-#define IC_THREADS 256                         // threads per CTA: 256 (2 CTAs / SM) or 128 (4 CTAs / SM)
+#define IC_THREADS 256                         // threads per CTA, 2 CTAs / SM (4 CTAs of 128 threads measured: no gain)
 #endif
 constexpr int IC_NSTRIP = IC_THREADS / 32;     // strips (8 rows x 32 columns) staged at a time: one per warp in phase B
 constexpr int IC_ROWS = IC_NSTRIP * 8;         // staged rows
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
 #undef PHASE_B_TILE
 }
 
-// two CTAs x (56 KB staged tile + 11 KB scalars + 1 KB reserved) = 138 KB -> the 164 KB shared-memory configuration, which
+// two CTAs x (60 KB staged strips + 11 KB scalars + 1 KB reserved) = 144 KB -> the 164 KB shared-memory configuration, which
 // leaves 92 KB of L1 for phase A's stencil reuse (measured: below ~90 KB of L1 the matvec phase loses 35 %)
 constexpr int IC_CARVEOUT_PCT = 64;
 
