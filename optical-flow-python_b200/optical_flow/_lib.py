@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200FLOW_LIB", os.path.join(os.path.dirname(_HERE), "libb200flow.so"))
 
 EINVAL, ECUDA, ENOCONV = -1, -2, -3
+# most page-locked host memory one context hands out as result buffers (Context.pinned_empty)
+PINNED_CAP_BYTES = int(os.environ.get("B200FLOW_PINNED_CAP_MB", "2048")) << 20
 
 
 class Penalty(C.Structure):
@@ -185,20 +187,27 @@ class Context:
         """Uninitialised C-contiguous NumPy array in page-locked host memory (cudaHostAlloc), so that the device->host
         copy of a result is one DMA instead of a staged copy into freshly mapped pageable pages.  The memory goes back to
         a per-context free list when the array (and every view of it) is garbage collected and is handed out again for
-        the next request of the same size: a loop of `uv = estimate_flow_batch(...)` allocates twice and then recycles."""
+        the next request of the same size: a loop of `uv = estimate_flow_batch(...)` allocates twice and then recycles.
+        A caller that keeps many results alive is not allowed to pin the host: beyond PINNED_CAP_BYTES of page-locked
+        memory owned by this context the array is an ordinary pageable np.empty."""
         shape = tuple(int(v) for v in np.atleast_1d(shape))
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        count = int(np.prod(shape))
+        nbytes = count * np.dtype(dtype).itemsize
         pool = self.__dict__.setdefault("_pinned_free", {})
         free = pool.setdefault(nbytes, [])
         if free:
             addr = free.pop()
         else:
+            owned = self.__dict__.get("_pinned_owned", 0)
+            if owned + nbytes > PINNED_CAP_BYTES:
+                return np.empty(shape, dtype=dtype)
             p = _vp()
             self.call("b200flow_host_alloc", C.c_ulonglong(max(nbytes, 1)), C.byref(p))
             addr = p.value
+            self._pinned_owned = owned + nbytes
         buf = (C.c_char * max(nbytes, 1)).from_address(addr)
         weakref.finalize(buf, free.append, addr)          # recycled, not freed: pinning 80 MB costs ~10 ms
-        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
 _tls = threading.local()

@@ -200,3 +200,11 @@ def test_pinned_result_buffers_are_recycled_only_when_released():
     gc.collect()
     c = f.pinned_empty((4, 5, 2))                 # released: recycled, no new allocation
     assert c.ctypes.data == addr and f.n == 2
+    # a caller hoarding results cannot pin the host: past the cap the buffers are ordinary pageable arrays
+    old_cap, _lib.PINNED_CAP_BYTES = _lib.PINNED_CAP_BYTES, 3 * 4 * 5 * 2 * 8
+    try:
+        d = f.pinned_empty((4, 5, 2))             # third owned buffer: still pinned
+        e = f.pinned_empty((4, 5, 2))             # would be the fourth: pageable
+        assert f.n == 3 and e.shape == (4, 5, 2) and e.flags["OWNDATA"] and not d.flags["OWNDATA"]
+    finally:
+        _lib.PINNED_CAP_BYTES = old_cap
