@@ -31,6 +31,18 @@ def test_e2e_well_posed_presets(stages, preset, capsys):
     assert_close(uv, g["uv"], E2E_TOL, "estimate_flow(%s)" % preset)
 
 
+@pytest.mark.parametrize("precision", ["mixed-jacobi", "fp64"])
+@pytest.mark.parametrize("preset", ["hs", "ba", "classic+nl-fast"])
+def test_e2e_solver_variants(stages, preset, precision):
+    """The reported solver variants (block-Jacobi mixed precision, all-fp64) behind the same fp64 true-residual
+    criterion: same final flow as the reference, like the IC-preconditioned default above."""
+    from optical_flow import estimate_flow
+    g = load_golden("e2e_%s.npz" % preset.replace("+", "p"))
+    im1, im2 = _crop(stages)
+    uv = estimate_flow(im1, im2, preset, {"solver_precision": precision})
+    assert_close(uv, g["uv"], E2E_TOL, "estimate_flow(%s, solver_precision=%s)" % (preset, precision))
+
+
 def test_e2e_gray_input(stages):
     """2-D gray input: classic+nl uses the gray frame itself as the 1-channel colour guide (interface.py:62-64)."""
     from optical_flow import estimate_flow
