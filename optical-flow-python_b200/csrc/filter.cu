@@ -334,6 +334,7 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
   }
   double L = next_below((double)flo), R = (double)fhi;   // open-closed value bracket: S(L) = 0 < half <= S(R) = total
   int nL = 0, nR = n;                                    // samples <= L, <= R
+  unsigned FL = 0u;                                      // fixed-point lower bound of S(L): S(L) * 2^22 / total in [FL, FL + nL]
   while (nR - nL > 32) {
     double p = 0.5 * (L + R);
     bool snap = !(p > L && p < R);
@@ -349,7 +350,7 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
       else if (f + (unsigned)c + 4u < WM_HALF_FIX) ge = false;
       else ge = exact_cum_weight<NPL>(x, w, p) >= half;    // too close to call in fixed point
       if (ge) { snap = c == nR; R = p; nR = c; }
-      else { snap = c == nL; L = p; nL = c; }
+      else { snap = c == nL; L = p; nL = c; FL = f; }
     }
     if (snap) {
       // a = smallest sample > L, b = largest sample <= R  (both exist: the bracket holds weight)
@@ -369,43 +370,56 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
       L = next_below(a); R = b;            // no sample lies in (old L, new L]: S(L) and the counts are unchanged
     }
   }
-  double SL = nL > 0 ? exact_cum_weight<NPL>(x, w, L) : 0.0;   // S(L), exactly, for the final evaluation
-  // stage 2: compact the survivors (L < x <= R), one per lane
+  // stage 2: compact the survivors (L < x <= R), one per lane, each with its fixed-point weight
   int cnt = 0;
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int k = 0; k < NPL; ++k) {
     const bool in = x[k] > L && x[k] <= R;
     const unsigned m = __ballot_sync(0xffffffffu, in);
-    if (in) scratch[cnt + __popc(m & lt)] = make_double2(x[k], w[k]);
+    if (in) scratch[cnt + __popc(m & lt)] = make_double2(x[k], __hiloint2double(0, (int)pk[k]));
     cnt += __popc(m);
   }
   __syncwarp();
   bool valid = lane < cnt;
   const double2 me = valid ? scratch[lane] : make_double2(INFINITY, 0.0);
+  const unsigned mypk = (unsigned)__double2loint(me.y);
   __syncwarp();
-  // stage 3a: bisection on the compacted set
+  // stage 3a: bisection on the compacted set, still in fixed point (S(p) * 2^22 / total in [FL + f, FL + f + nL + c])
   while (cnt > 8) {
     const double p = 0.5 * (L + R);
     if (!(p > L && p < R)) break;
     const bool le = valid && me.x <= p;
-    double s = le ? me.y : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    s += SL;
-    const int c = __popc(__ballot_sync(0xffffffffu, le));
+    const unsigned acc = __reduce_add_sync(0xffffffffu, le ? mypk : 0u);
+    const int c = (int)(acc & 511u);
     if (c == 0 || c == cnt) break;         // nothing separated (cluster): let the all-pairs pass sort it out
-    if (s >= half) { R = p; valid = le; cnt = c; }
-    else { L = p; SL = s; valid = valid && !le; cnt -= c; }
+    const unsigned f = FL + (acc >> 9);
+    bool ge;
+    if (f >= WM_HALF_FIX + 4u) ge = true;
+    else if (f + (unsigned)(nL + c) + 4u < WM_HALF_FIX) ge = false;
+    else ge = exact_cum_weight<NPL>(x, w, p) >= half;
+    if (ge) { R = p; valid = le; cnt = c; }
+    else { L = p; FL = f; nL += c; valid = valid && !le; cnt -= c; }
   }
-  // stage 3b: S at every survivor, all pairs
-  double c = SL;
+  // stage 3b: S at every survivor from an all-pairs pass over the survivors, in fixed point; a survivor whose S is too
+  // close to half to call (true value in [f, f + count]) gets the exact fp64 sum over the whole window instead
+  unsigned acc = 0u;
   for (unsigned m = __ballot_sync(0xffffffffu, valid); m; m &= m - 1) {
     const int j = __ffs(m) - 1;
-    const double xj = __shfl_sync(0xffffffffu, me.x, j), wj = __shfl_sync(0xffffffffu, me.y, j);
-    if (xj <= me.x) c += wj;
+    const double xj = __shfl_sync(0xffffffffu, me.x, j);
+    const unsigned pj = __shfl_sync(0xffffffffu, mypk, j);
+    if (xj <= me.x) acc += pj;
   }
-  double ans = (valid && c >= half) ? me.x : INFINITY;   // some survivor qualifies: S(largest survivor) = S(R) >= half
+  const unsigned fi = FL + (acc >> 9), ci = (unsigned)nL + (acc & 511u);
+  bool ge = fi >= WM_HALF_FIX + 4u;
+  const bool unsure = valid && !ge && !(fi + ci + 4u < WM_HALF_FIX);
+  for (unsigned m = __ballot_sync(0xffffffffu, unsure); m; m &= m - 1) {
+    const int j = __ffs(m) - 1;
+    const double sj = exact_cum_weight<NPL>(x, w, __shfl_sync(0xffffffffu, me.x, j));
+    if (lane == j) ge = sj >= half;
+  }
+  const bool c_ok = ge;                                    // S(own value) >= half
+  double ans = (valid && c_ok) ? me.x : INFINITY;          // some survivor qualifies: S(largest survivor) = S(R) >= half
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double t = __shfl_xor_sync(0xffffffffu, ans, o);
