@@ -161,6 +161,38 @@ def test_zero_motion_gives_zero_increment(precision):
     assert np.isfinite(x).all() and np.abs(x).max() < 1e-12
 
 
+@pytest.mark.parametrize("h,w", [(19, 37), (9, 33), (26, 70)])
+def test_exact_solvers_on_ragged_sizes_vs_dense_solve(h, w):
+    """Sizes that are not multiples of the solver's 8 x 32 strips (partial strips, a single strip row, one extra
+    column): the operator is probed column by column into a dense matrix, solved with LAPACK, and compared with the
+    three device solvers."""
+    import synth
+    from optical_flow import load_of_method
+    from optical_flow.utils.derivatives import partial_deriv
+    im1, im2, _ = synth.gray_pair(h, w, seed=h * w)
+    images = np.stack([im1, im2], axis=2)
+    ope = load_of_method("classic+nl")
+    ope.images = images
+    rng = np.random.default_rng(h + w)
+    uv = 0.3 * rng.standard_normal((h, w, 2))
+    It, Ix, Iy = partial_deriv(images, uv, ope.interpolation_method, ope.deriv_filter, 0.5)
+    A, b, _, _ = ope.flow_operator(uv, np.zeros_like(uv), It, Ix, Iy)
+    n = 2 * h * w
+    dense = np.empty((n, n))
+    e = np.zeros(n)
+    for k in range(n):
+        e[k] = 1.0
+        dense[:, k] = A @ e
+        e[k] = 0.0
+    assert np.abs(dense - dense.T).max() <= 1e-12 * np.abs(dense).max()          # symmetric operator
+    want = np.linalg.solve(dense, b).reshape((h, w, 2), order="F")
+    for precision in ("mixed", "mixed-jacobi", "fp64"):
+        ope.solver_precision = precision
+        x = ope._solve_linear_system(A, b, (h, w, 2))
+        assert_close(x, want, 2e-6, "%dx%d %s solve vs dense LAPACK solve (pcg %r)" % (w, h, precision, ope.last_stats))
+        assert ope.last_stats["relres"] <= 1e-10
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the reference's own approximate solver modes (SURVEY 8f row 2)
 # ---------------------------------------------------------------------------------------------------------------
