@@ -428,8 +428,11 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
   return ans;
 }
 
+#ifndef WM_MINB
+#define WM_MINB 3                // CTAs per SM the register budget is cut for: 3 (80 registers) 106 ms of filter time per bench step, 2 (128) 116 ms, 4 (64) 126 ms
+#endif
 template <int NPL>
-__global__ void __launch_bounds__(WM_WARPS * 32, 3) wmedian_kernel(const double2 *__restrict__ cand,
+__global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const double2 *__restrict__ cand,
                                                                   const double2 *__restrict__ base,
                                                                   const double *__restrict__ color, int C,
                                                                   const double *__restrict__ occ, int H, int W, int hsz,
