@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--solver-precision", default="mixed", choices=["mixed", "mixed-jacobi", "fp64"],
                     help="mixed: fp32 Krylov vectors with fp64 reliable updates, tile-local block-IC(0) preconditioner "
                          "(default); mixed-jacobi: same with the block-Jacobi preconditioner; fp64: all-fp64 PCG (variants)")
+    ap.add_argument("--split", type=int, default=None,
+                    help="concurrent sub-batches per GPU (b200flow_ctx_set_split); default: the library's default")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -249,6 +251,8 @@ def main():
 
     ims1, ims2, flow_gt = make_batch(B, 3 + rank * B)            # every rank its own pairs (weak scaling)
     ctx = _lib.default_context(local_rank)
+    if args.split is not None:
+        ctx.set_split(args.split)
     PCG_BYTES_PER_PIXEL_ITER = PCG_BYTES[args.solver_precision]
     ope = load_of_method(METHOD)
     ope.solver_precision = args.solver_precision

@@ -95,6 +95,12 @@ int  b200flow_ctx_create(int device, b200flow_ctx **out);
 void b200flow_ctx_destroy(b200flow_ctx *ctx);
 const char *b200flow_last_error(const b200flow_ctx *ctx);   /* ctx may be NULL: last creation error */
 int  b200flow_ctx_set_timing(b200flow_ctx *ctx, int enabled);   /* per-stage CUDA-event timing into b200flow_stats */
+/* Concurrent sub-batches (no counterpart in the reference, which is single threaded): the batched entry points cut a
+ * batch of B pairs into `groups` groups that run the coarse-to-fine loop (hs.py:49-142, ba.py:57-206, classic_nl.py:89-277)
+ * on their own CUDA streams, so that the HBM-bound solver of one group overlaps the issue-bound weighted median of
+ * another.  solver_ctas_per_sm = CTAs per SM each group's persistent solver takes (0: an equal share).  groups = 1
+ * (default) is the plain single-stream pipeline.  Results are identical either way (pairs are independent). */
+int  b200flow_ctx_set_split(b200flow_ctx *ctx, int groups, int solver_ctas_per_sm);
 int  b200flow_ctx_sync(b200flow_ctx *ctx);
 void *b200flow_ctx_stream(b200flow_ctx *ctx);               /* the cudaStream_t, for torch / event interop */
 int  b200flow_ctx_num_sms(const b200flow_ctx *ctx);

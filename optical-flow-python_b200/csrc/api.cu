@@ -58,6 +58,8 @@ int b200flow_ctx_create(int device, b200flow_ctx **out) {
     delete ctx;
     return B200FLOW_ECUDA;
   }
+  if (const char *sp = getenv("B200FLOW_SPLIT")) ctx->nsplit = atoi(sp) > 1 ? atoi(sp) : 1;   // tuning / experiments
+  if (const char *sc = getenv("B200FLOW_SOLVER_CTAS")) ctx->solver_ctas_per_sm = atoi(sc) > 0 ? atoi(sc) : 0;
   *out = ctx;
   return 0;
 }
@@ -65,6 +67,14 @@ int b200flow_ctx_create(int device, b200flow_ctx **out) {
 void b200flow_ctx_destroy(b200flow_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (auto *c : ctx->subs) {
+    cudaStreamSynchronize(c->stream);
+    for (auto &k : c->chunks) cudaFree(k.base);
+    cudaStreamDestroy(c->stream);
+    delete c;
+  }
+  for (auto e : ctx->ev_join) cudaEventDestroy(e);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaStreamSynchronize(ctx->stream);
   for (auto &c : ctx->chunks) cudaFree(c.base);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -77,6 +87,15 @@ const char *b200flow_last_error(const b200flow_ctx *ctx) { return ctx ? ctx->err
 int b200flow_ctx_set_timing(b200flow_ctx *ctx, int enabled) {
   if (!ctx) return B200FLOW_EINVAL;
   ctx->timing = enabled != 0;
+  return 0;
+}
+
+int b200flow_ctx_set_split(b200flow_ctx *ctx, int groups, int solver_ctas_per_sm) {
+  if (!ctx) return B200FLOW_EINVAL;
+  if (groups < 1 || groups > 8 || solver_ctas_per_sm < 0)
+    return set_err(ctx, B200FLOW_EINVAL, "concurrent sub-batches: groups %d (1..8), solver CTAs per SM %d (>= 0)", groups, solver_ctas_per_sm);
+  ctx->nsplit = groups;
+  ctx->solver_ctas_per_sm = solver_ctas_per_sm;
   return 0;
 }
 

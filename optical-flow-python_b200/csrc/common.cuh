@@ -25,6 +25,20 @@ struct b200flow_ctx {
   // statistics
   int launches = 0;
   bool timing = false;
+  // resident grid sizes of the persistent solver kernels on this device (filled once by solve.cu; 0 = not yet queried)
+  int grid_pcg = 0, grid_mixed = 0, grid_ic = 0;
+  int ic_ctas_per_sm = 0;           // occupancy of pcg_ic_kernel as reported by the runtime
+  // Concurrent sub-batches (pipeline.cu, run_pipeline_split): a batch of B pairs is cut into `nsplit` groups that run the
+  // whole coarse-to-fine loop on their own stream and arena, so that the bandwidth-bound solver of one group overlaps the
+  // issue-bound weighted median of another.  The persistent solver then takes solver_ctas_per_sm CTAs per SM (so that the
+  // solvers of all groups can be resident together) and is launched without the cooperative attribute.
+  int nsplit = 1;
+  int solver_ctas_per_sm = 0;       // 0 = all the runtime allows
+  bool plain_solver_launch = false; // children of a split context: <<<>>> instead of cudaLaunchCooperativeKernel
+  b200flow_ctx *parent = nullptr;
+  std::vector<b200flow_ctx *> subs; // child contexts (own stream + arena), created on demand
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_join;
 };
 
 namespace bf {

@@ -234,7 +234,10 @@ int k_sub(b200flow_ctx *ctx, const double2 *a, const double2 *b, double2 *out, l
 //   Tile of colour / occ / flow staged in shared memory with the NumPy 'reflect' (mirror, no edge repeat)
 //   boundary.  Compute-bound (fp64 compare/add/min/max + shuffles), ~64 B/pixel of HBM traffic.
 // ------------------------------------------------------------------------------------------------
-constexpr int WM_TW = 16, WM_TH = 8, WM_WARPS = 8;
+#ifndef WM_WARPS_N
+#define WM_WARPS_N 8
+#endif
+constexpr int WM_TW = 16, WM_TH = WM_WARPS_N, WM_WARPS = WM_WARPS_N;   // one warp per tile row
 
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
@@ -526,6 +529,9 @@ static int launch_wmedian(b200flow_ctx *ctx, const double2 *cand, const double2 
   size_t smem = (size_t)SW * SH * 6 * sizeof(double) + WM_WARPS * 32 * sizeof(double2);
   if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
   BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // same shared-memory configuration as the persistent solver (solve_ic.cu IC_CARVEOUT_PCT): with concurrent sub-batches
+  // CTAs of both kernels share an SM, which they only can under one L1 / shared-memory split
+  BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributePreferredSharedMemoryCarveout, 64));
   dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
   double inv2s2 = 1.0 / (2.0 * (sigma_i * sigma_i));
   BF_LAUNCH(ctx, (wmedian_kernel<NPL>), grd, WM_WARPS * 32, smem, cand, base, color, C, occ, H, W, hsz, inv2s2, out);

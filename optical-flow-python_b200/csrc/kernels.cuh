@@ -85,6 +85,7 @@ int k_pcg_solve(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, i
 int k_pcg_solve_async(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                       long long *stats_dev);
 int k_operator_apply(b200flow_ctx *, LinSys sys, const double2 *x, double2 *Ax, double2 *diag);
+int pcg_ic_grid(b200flow_ctx *ctx, int *grid_out);   // solve_ic.cu: resident grid of pcg_ic_kernel (fills ctx->ic_ctas_per_sm)
 
 // ---- filter.cu
 // out = base + (median(base + clip(x)) - base) when x != null (BA update, ba.py:186-204), else out = median(base)

@@ -3,6 +3,8 @@
 // Replaces HSOpticalFlow.compute_flow/compute_flow_base (hs.py:49-142), BAOpticalFlow (ba.py:57-206) and
 // ClassicNLOpticalFlow (classic_nl.py:89-277).  Every buffer is allocated once at full resolution from the
 // context arena and reused by every level / warp iteration.
+#include <algorithm>
+#include <utility>
 #include "kernels.cuh"
 
 namespace bf {
@@ -41,12 +43,18 @@ __global__ void fill_int_kernel(int *p, int n, int v) {
 }
 
 // per-stage CUDA-event timing (only when ctx->timing): events are recorded on the stream and resolved once at the end
+// as intervals relative to a base event, so that the spans of concurrent sub-batches can be merged (union per category)
+struct Interval { int cat; float a, b; };
 struct StageTimer {
-  b200flow_ctx *ctx;
-  bool on;
+  b200flow_ctx *ctx = nullptr;
+  bool on = false;
   struct Span { cudaEvent_t a, b; int cat; };
   std::vector<Span> spans;
-  explicit StageTimer(b200flow_ctx *c) : ctx(c), on(c->timing) {}
+  StageTimer() {}
+  void init(b200flow_ctx *c) { ctx = c; on = c->timing; }
+  ~StageTimer() { clear(); }
+  StageTimer(const StageTimer &) = delete;
+  StageTimer &operator=(const StageTimer &) = delete;
   void begin(int cat) {
     if (!on) return;
     Span s;
@@ -60,17 +68,33 @@ struct StageTimer {
     if (!on) return;
     cudaEventRecord(spans.back().b, ctx->stream);
   }
-  void resolve(double ms[4]) {
-    for (int i = 0; i < 4; ++i) ms[i] = 0.0;
+  void resolve(cudaEvent_t base, std::vector<Interval> *out) {
     for (auto &s : spans) {
-      float t = 0.f;
-      if (on && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms[s.cat] += t;
-      cudaEventDestroy(s.a);
-      cudaEventDestroy(s.b);
+      float ta = 0.f, tb = 0.f;
+      if (on && cudaEventElapsedTime(&ta, base, s.a) == cudaSuccess && cudaEventElapsedTime(&tb, base, s.b) == cudaSuccess)
+        out->push_back({s.cat, ta, tb});
     }
+    clear();
+  }
+  void clear() {
+    for (auto &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     spans.clear();
   }
 };
+// total length of the union of the intervals of one category (ms)
+static double union_ms(std::vector<Interval> v, int cat) {
+  std::vector<std::pair<float, float>> w;
+  for (auto &i : v) if (i.cat == cat && i.b > i.a) w.push_back({i.a, i.b});
+  std::sort(w.begin(), w.end());
+  double total = 0.0;
+  float ca = 0.f, cb = -1.f;
+  for (auto &i : w) {
+    if (cb < ca || i.first > cb) { if (cb > ca) total += cb - ca; ca = i.first; cb = i.second; }
+    else if (i.second > cb) cb = i.second;
+  }
+  if (cb > ca) total += cb - ca;
+  return total;
+}
 enum { T_PRE = 0, T_WARP = 1, T_SOLVE = 2, T_FILTER = 3 };
 
 int check_params(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C) {
@@ -120,30 +144,58 @@ int alloc_linsys(b200flow_ctx *ctx, int B, int H, int W, LinSys *s) {
   return 0;
 }
 
+// what pipeline_issue leaves behind for pipeline_finish (events are released by the destructor on every exit path)
+struct PipelineRun {
+  StageTimer tm;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long long *dstats = nullptr;
+  int solves = 0, launches0 = 0;
+  PipelineRun() {}
+  PipelineRun(const PipelineRun &) = delete;
+  PipelineRun &operator=(const PipelineRun &) = delete;
+  ~PipelineRun() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+};
+
+struct RunResult {
+  long long hstats[4] = {0, 0, 0, 0};
+  std::vector<Interval> iv;       // stage spans relative to the base event (ms)
+  float t0 = 0.f, t1 = 0.f;       // begin / end of the run relative to the base event
+  int solves = 0, launches = 0;
+};
+
+// Queues the whole coarse-to-fine loop of B pairs on ctx->stream; never synchronises (unless B200FLOW_TRACE is set).
 // gray_planar: [B][2*NC][H][W] -- NC channels of frame 1, then NC channels of frame 2 (NC = 1 for gray frames)
-int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int NC, int C, const double *gray_planar,
-                 const double *color_planar, const double2 *init, double2 *uv_out, b200flow_stats *stats) {
+static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int NC, int C,
+                          const double *gray_planar, const double *color_planar, const double2 *init, double2 *uv_out,
+                          PipelineRun *run) {
   BF_TRY(check_params(ctx, p, B, H, W, C));
   if (NC < 1 || NC > 8) return set_err(ctx, B200FLOW_EINVAL, "channels per frame NC=%d unsupported (1..8)", NC);
   const int NP = 2 * NC;                                  // image planes per pair
   const long long HW = (long long)H * W;
   const size_t N = (size_t)B * HW;
   const bool hs = p->method == B200FLOW_HS, cnl = p->method == B200FLOW_CLASSICNL;
-  const int launches0 = ctx->launches;
+  run->launches0 = ctx->launches;
   const bool trace = getenv("B200FLOW_TRACE") != nullptr;
-  StageTimer tm(ctx);
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  StageTimer &tm = run->tm;
+  tm.init(ctx);
   if (ctx->timing) {
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
-    cudaEventRecord(ev0, ctx->stream);
+    cudaEventCreate(&run->ev0);
+    cudaEventCreate(&run->ev1);
+    cudaEventRecord(run->ev0, ctx->stream);
   }
 
   // ---- pre-processing: texture or [0,255] scaling (joint over the two frames of a pair) ----
   tm.begin(T_PRE);
   double *pre;
   BF_TRY(arena_alloc(ctx, &pre, NP * N));
-  if (p->texture > 0) BF_TRY(k_rof_texture(ctx, gray_planar, pre, B, NP, H, W, p->rof_theta, p->rof_iters, p->alp));
+  // Horn-Schunck calls structure_texture_decomposition_rof(self.images) with the function's own defaults
+  // (hs.py:66-67: theta 1/8, 100 iterations, alp 0.95), whatever self.alp says; BA / Classic+NL pass self.alp
+  if (p->texture > 0)
+    BF_TRY(k_rof_texture(ctx, gray_planar, pre, B, NP, H, W, hs ? 1.0 / 8 : p->rof_theta, hs ? 100 : p->rof_iters,
+                         hs ? 0.95 : p->alp));
   else if (p->texture == 0) BF_TRY(k_minmax_scale(ctx, gray_planar, pre, B, NP * HW, 0.0, 255.0));
   else BF_CUDA(ctx, cudaMemcpyAsync(pre, gray_planar, NP * N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 
@@ -258,7 +310,7 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
           tm.begin(T_FILTER);
           if (hs) {
             BF_TRY(k_hs_norm_gate(ctx, x, B, hw, active, nscratch));
-            if (have_median) {
+            if (have_median && p->mf_iter >= 1) {     // hs.py:137-140: mf_iter passes, none at all when mf_iter < 1
               BF_TRY(k_median_uv(ctx, cur, x, p->limit_update, active, nxt, B, h, w, mh, mw, 1));
               for (int m = 1; m < p->mf_iter; ++m) {
                 std::swap(cur, nxt);
@@ -303,30 +355,117 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
     std::swap(cur, nxt);
   }
   BF_CUDA(ctx, cudaMemcpyAsync(uv_out, cur, N * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
-  if (ctx->timing) cudaEventRecord(ev1, ctx->stream);
+  if (ctx->timing) cudaEventRecord(run->ev1, ctx->stream);
+  run->dstats = dstats;
+  run->solves = solves;
+  return 0;
+}
 
-  long long hstats[4] = {0, 0, 0, 0};
-  if (stats || ctx->timing) {
-    BF_CUDA(ctx, cudaMemcpyAsync(hstats, dstats, sizeof hstats, cudaMemcpyDeviceToHost, ctx->stream));
+// Waits for a queued run (only when its outcome is wanted) and collects the device-side statistics and stage spans.
+static int pipeline_finish(b200flow_ctx *ctx, PipelineRun *run, bool want, cudaEvent_t base, RunResult *res) {
+  res->solves = run->solves;
+  res->launches = ctx->launches - run->launches0;
+  if (want || ctx->timing) {
+    BF_CUDA(ctx, cudaMemcpyAsync(res->hstats, run->dstats, sizeof res->hstats, cudaMemcpyDeviceToHost, ctx->stream));
     BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
-  double ms[4] = {0, 0, 0, 0};
-  tm.resolve(ms);
-  if (stats) {
-    stats->solves = solves;
-    stats->pcg_iters = hstats[0];
-    stats->not_converged = (int)hstats[1];
-    stats->pcg_pixel_iters = hstats[3];
-    stats->kernel_launches = ctx->launches - launches0;
-    stats->pre_ms = ms[T_PRE]; stats->warp_ms = ms[T_WARP]; stats->solver_ms = ms[T_SOLVE]; stats->filter_ms = ms[T_FILTER];
-    stats->total_ms = 0.0;
-    if (ctx->timing) {
-      float t = 0.f;
-      cudaEventElapsedTime(&t, ev0, ev1);
-      stats->total_ms = t;
-    }
+  if (ctx->timing) {
+    if (!base) base = run->ev0;
+    run->tm.resolve(base, &res->iv);
+    cudaEventElapsedTime(&res->t0, base, run->ev0);
+    cudaEventElapsedTime(&res->t1, base, run->ev1);
   }
-  if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+  return 0;
+}
+
+static void fill_stats(b200flow_stats *stats, const std::vector<RunResult> &rr, bool timing) {
+  if (!stats) return;
+  stats->solves = 0; stats->pcg_iters = 0; stats->not_converged = 0; stats->pcg_pixel_iters = 0; stats->kernel_launches = 0;
+  std::vector<Interval> all;
+  float t0 = 0.f, t1 = 0.f;
+  bool first = true;
+  for (auto &r : rr) {
+    stats->solves = r.solves > stats->solves ? r.solves : stats->solves;              // every group runs the same loop
+    stats->pcg_iters = r.hstats[0] > stats->pcg_iters ? r.hstats[0] : stats->pcg_iters; // slowest group
+    stats->not_converged += (int)r.hstats[1];
+    stats->pcg_pixel_iters += r.hstats[3];
+    stats->kernel_launches += r.launches;
+    all.insert(all.end(), r.iv.begin(), r.iv.end());
+    if (first || r.t0 < t0) t0 = r.t0;
+    if (first || r.t1 > t1) t1 = r.t1;
+    first = false;
+  }
+  // with concurrent groups the spans of one category overlap in time: report the time during which at least one group
+  // was in that stage (for one group this is the plain sum)
+  stats->pre_ms = union_ms(all, T_PRE); stats->warp_ms = union_ms(all, T_WARP);
+  stats->solver_ms = union_ms(all, T_SOLVE); stats->filter_ms = union_ms(all, T_FILTER);
+  stats->total_ms = timing ? (double)(t1 - t0) : 0.0;
+}
+
+static int ensure_subs(b200flow_ctx *ctx, int ns) {
+  if (!ctx->ev_fork) BF_CUDA(ctx, cudaEventCreate(&ctx->ev_fork));
+  while ((int)ctx->subs.size() < ns) {
+    b200flow_ctx *c = new b200flow_ctx();
+    c->device = ctx->device;
+    c->num_sms = ctx->num_sms;
+    c->parent = ctx;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return set_err(ctx, B200FLOW_ECUDA, "cudaStreamCreate for a sub-batch failed");
+    }
+    ctx->subs.push_back(c);
+    cudaEvent_t e;
+    BF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ev_join.push_back(e);
+  }
+  return 0;
+}
+
+int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int NC, int C, const double *gray_planar,
+                 const double *color_planar, const double2 *init, double2 *uv_out, b200flow_stats *stats) {
+  int ns = ctx->nsplit < 1 ? 1 : ctx->nsplit;
+  if (ns > B) ns = B;
+  if (p && p->solver != B200FLOW_SOLVER_EXACT_IC) ns = 1;     // only pcg_ic_kernel is sized for co-residency
+  if (getenv("B200FLOW_TRACE")) ns = 1;
+  std::vector<RunResult> rr(ns);
+  if (ns == 1) {
+    PipelineRun run;
+    BF_TRY(pipeline_issue(ctx, p, B, H, W, NC, C, gray_planar, color_planar, init, uv_out, &run));
+    BF_TRY(pipeline_finish(ctx, &run, stats != nullptr, nullptr, &rr[0]));
+    fill_stats(stats, rr, ctx->timing);
+    return 0;
+  }
+  // ---- concurrent sub-batches: group g = pairs [g B / ns, (g + 1) B / ns) on its own stream and arena ----
+  BF_TRY(ensure_subs(ctx, ns));
+  int nb = 0;
+  BF_TRY(pcg_ic_grid(ctx, &nb));                              // fills ctx->ic_ctas_per_sm
+  const long long HW = (long long)H * W;
+  BF_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  std::vector<PipelineRun> runs(ns);
+  for (int g = 0; g < ns; ++g) {
+    b200flow_ctx *c = ctx->subs[g];
+    const int b0 = (int)((long long)g * B / ns), b1 = (int)((long long)(g + 1) * B / ns);
+    arena_reset(c);
+    c->timing = ctx->timing;
+    c->plain_solver_launch = true;
+    c->solver_ctas_per_sm = ctx->solver_ctas_per_sm > 0 ? ctx->solver_ctas_per_sm
+                                                        : (ctx->ic_ctas_per_sm / ns > 0 ? ctx->ic_ctas_per_sm / ns : 1);
+    if (c->solver_ctas_per_sm * ns > ctx->ic_ctas_per_sm)
+      return set_err(ctx, B200FLOW_EINVAL, "%d concurrent sub-batches x %d solver CTAs per SM exceed the %d the device holds",
+                     ns, c->solver_ctas_per_sm, ctx->ic_ctas_per_sm);
+    BF_CUDA(ctx, cudaStreamWaitEvent(c->stream, ctx->ev_fork, 0));
+    int rc = pipeline_issue(c, p, b1 - b0, H, W, NC, C, gray_planar + (size_t)b0 * 2 * NC * HW,
+                            color_planar ? color_planar + (size_t)b0 * C * HW : nullptr, init ? init + (size_t)b0 * HW : nullptr,
+                            uv_out + (size_t)b0 * HW, &runs[g]);
+    if (rc < 0) { ctx->err = c->err; return rc; }
+    BF_CUDA(ctx, cudaEventRecord(ctx->ev_join[g], c->stream));
+    BF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
+  }
+  for (int g = 0; g < ns; ++g) {
+    int rc = pipeline_finish(ctx->subs[g], &runs[g], stats != nullptr, ctx->ev_fork, &rr[g]);
+    if (rc < 0) { ctx->err = ctx->subs[g]->err; return rc; }
+  }
+  fill_stats(stats, rr, ctx->timing);
   return 0;
 }
 

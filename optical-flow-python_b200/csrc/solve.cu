@@ -412,6 +412,10 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
   double *part_a = P.w.partial;                         // [B][G]  p.Ap
   double *part_b = P.w.partial + (long long)B * G;      // [B][G]  r.z
   double *part_c = P.w.partial + 2LL * B * G;           // [B][G]  r.r
+  // reliable-update partials get their own slices: a fast CTA reaches its reliable update while a slow CTA is still
+  // summing the phase-B slots (no grid barrier in between), so it must not write part_b / part_c there
+  double *part_d = P.w.partial + 3LL * B * G;           // [B][G]  r.z of the replaced residual
+  double *part_e = P.w.partial + 4LL * B * G;           // [B][G]  r.r of the replaced residual
   float *Minv = P.w.Minv;
   float2 *r = P.m.r, *z = P.m.z, *Ap = P.m.Ap, *y = P.m.y;
   float2 *pold = P.m.p, *pnew = P.m.p2;
@@ -647,10 +651,10 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
           acc_rz += d.x; acc_rr += d.y;
         }
         block_sum2(acc_rz, acc_rr, sm_red);
-        if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
+        if (tid == 0) { part_d[(long long)b * G + cta] = acc_rz; part_e[(long long)b * G + cta] = acc_rr; }
       }
       grid.sync();
-      REDUCE_ALL(part_b, part_c, 3)
+      REDUCE_ALL(part_d, part_e, 3)
       int fin = 0;
       if (tid < B && s_state[tid] == 3) {
         const int b = tid;
@@ -808,18 +812,21 @@ size_t pcg_work_bytes(const b200flow_ctx *ctx, int B, int H, int W) {
 }
 
 static int pcg_grid(b200flow_ctx *ctx, int *grid_out, int *grid_mixed_out) {
-  static int cached_dev = -1, cached = 0, cached_mixed = 0;
-  if (cached_dev != ctx->device) {
+  if (ctx->grid_pcg == 0) {          // per context: distinct contexts may live on different devices / host threads
     int nb = 0, nm = 0;
     BF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcg_kernel, PCG_THREADS, 0));
     BF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nm, pcg_mixed_kernel, PCG_THREADS, 0));
     if (nb < 1 || nm < 1) return set_err(ctx, B200FLOW_ECUDA, "pcg kernels cannot be made resident");
-    cached = nb * ctx->num_sms;
-    cached_mixed = nm * ctx->num_sms;
-    cached_dev = ctx->device;
+    ctx->grid_pcg = nb * ctx->num_sms;
+    ctx->grid_mixed = nm * ctx->num_sms;
   }
-  *grid_out = cached;
-  *grid_mixed_out = cached_mixed;
+  *grid_out = ctx->grid_pcg;
+  *grid_mixed_out = ctx->grid_mixed;
+  if (ctx->solver_ctas_per_sm > 0) {  // split context: leave room for the sibling groups' kernels
+    const int cap = ctx->solver_ctas_per_sm * ctx->num_sms;
+    if (*grid_out > cap) *grid_out = cap;
+    if (*grid_mixed_out > cap) *grid_mixed_out = cap;
+  }
   return 0;
 }
 
@@ -840,7 +847,7 @@ int pcg_work_alloc(b200flow_ctx *ctx, int B, int H, int W, PcgWork *w) {
   BF_TRY(arena_alloc(ctx, &w->Minv, 3 * n));
   BF_TRY(arena_alloc(ctx, &w->ic_c0, n));
   BF_TRY(arena_alloc(ctx, &w->ic_cw, n));
-  BF_TRY(arena_alloc(ctx, &w->partial, (size_t)4 * B * G));   // G = the larger of the two kernels' grids
+  BF_TRY(arena_alloc(ctx, &w->partial, (size_t)5 * B * G));   // five slices; G = the largest of the three kernels' grids
   BF_TRY(arena_alloc(ctx, &w->scal, (size_t)B));
   BF_TRY(arena_alloc(ctx, &w->flags, (size_t)(1 + 2 * B)));
   return 0;
@@ -898,6 +905,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
         cudaFuncSetAttribute(pcg_mixed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
       }
 #endif
+      if (ctx->plain_solver_launch) return set_err(ctx, B200FLOW_EINVAL, "concurrent sub-batches need solver_precision='mixed' (pcg_ic_kernel)");
       BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_mixed_kernel, dim3(G), dim3(PCG_THREADS), args, dyn, ctx->stream));
     }
   } else {
@@ -914,6 +922,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
                      sys.B, sys.H, sys.W);
     P.w.grid = G;
     void *args[] = {&P};
+    if (ctx->plain_solver_launch) return set_err(ctx, B200FLOW_EINVAL, "concurrent sub-batches need solver_precision='mixed' (pcg_ic_kernel)");
     BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_kernel, dim3(G), dim3(PCG_THREADS), args, 0, ctx->stream));
   }
   if (mode != PCG_MODE_SOR) ctx->launches++;

@@ -363,6 +363,10 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   double *part_a = P.w.partial;                         // [B][G]  p.Ap
   double *part_b = P.w.partial + (long long)B * G;      // [B][G]  r.z
   double *part_c = P.w.partial + 2LL * B * G;           // [B][G]  r.r
+  // reliable-update partials get their own slices: a fast CTA reaches its reliable update while a slow CTA is still
+  // summing the phase-B slots (no grid barrier in between), so it must not write part_b / part_c there
+  double *part_d = P.w.partial + 3LL * B * G;           // [B][G]  r.z of the replaced residual
+  double *part_e = P.w.partial + 4LL * B * G;           // [B][G]  r.r of the replaced residual
   float4 *C0 = P.w.ic_c0;                               // [n_all] {i11, i12, i22, bf16x2 {wuh, wvh}}: inverted IC pivot blocks + edges
   unsigned *CW = P.w.ic_cw;                             // [n_all] bf16x2 {wuv, wvv}
   float2 *r = P.m.r, *z = P.m.z, *Ap = P.m.Ap, *y = P.m.y;
@@ -692,10 +696,10 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
         __syncthreads();                       // r of the own strips is complete (same ownership in both passes)
         for (long long t = ta + ty; t < tb; t += IC_NSTRIP) PHASE_B_TILE(t, 0.f, false, acc_rz, acc_dummy)
         ic_block_sum2(acc_rz, acc_rr, sm_red);
-        if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
+        if (tid == 0) { part_d[(long long)b * G + cta] = acc_rz; part_e[(long long)b * G + cta] = acc_rr; }
       }
       IC_GRID_SYNC();
-      REDUCE_ALL(part_b, part_c, 3)
+      REDUCE_ALL(part_d, part_e, 3)
       int fin = 0;
       if (tid < B && s_state[tid] == 3) {
         const int b = tid;
@@ -761,8 +765,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
 constexpr int IC_CARVEOUT_PCT = 64;
 
 int pcg_ic_grid(b200flow_ctx *ctx, int *grid_out) {
-  static int cached_dev = -1, cached = 0;
-  if (cached_dev != ctx->device) {
+  if (ctx->grid_ic == 0) {            // per context (function attributes are per device; setting them again is harmless)
     int nb = 0;
     BF_CUDA(ctx, cudaFuncSetAttribute(pcg_ic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IC_SMEM));
     int carve = IC_CARVEOUT_PCT;
@@ -772,10 +775,12 @@ int pcg_ic_grid(b200flow_ctx *ctx, int *grid_out) {
     BF_CUDA(ctx, cudaFuncSetAttribute(pcg_ic_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     BF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcg_ic_kernel, IC_THREADS, IC_SMEM));
     if (nb < 1) return set_err(ctx, B200FLOW_ECUDA, "pcg_ic_kernel cannot be made resident");
-    cached = nb * ctx->num_sms;
-    cached_dev = ctx->device;
+    ctx->ic_ctas_per_sm = nb;
+    ctx->grid_ic = nb * ctx->num_sms;
   }
-  *grid_out = cached;
+  *grid_out = ctx->grid_ic;
+  if (ctx->solver_ctas_per_sm > 0 && *grid_out > ctx->solver_ctas_per_sm * ctx->num_sms)
+    *grid_out = ctx->solver_ctas_per_sm * ctx->num_sms;      // split context: the sibling groups' solvers are resident too
   return 0;
 }
 
@@ -796,7 +801,19 @@ int k_pcg_ic_launch(b200flow_ctx *ctx, MixParams P, int grid_max) {
   if (const char *dbg = getenv("B200FLOW_IC_DEBUG")) P.debug = atoi(dbg);
 #endif
   void *args[] = {&P};
-  BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_ic_kernel, dim3(G), dim3(IC_THREADS), args, IC_SMEM, ctx->stream));
+  if (ctx->plain_solver_launch) {
+    // split context (pipeline.cu): the groups' solver grids together never exceed what the device can hold and every
+    // other kernel of the library terminates on its own, so all CTAs become resident without the cooperative attribute
+    // (the kernel uses its own counter barrier, not cooperative_groups' grid.sync())
+#ifdef IC_CG_BARRIER
+    return set_err(ctx, B200FLOW_EINVAL, "IC_CG_BARRIER builds cannot run concurrent sub-batches");
+#else
+    pcg_ic_kernel<<<dim3(G), dim3(IC_THREADS), IC_SMEM, ctx->stream>>>(P);
+    BF_CUDA(ctx, cudaPeekAtLastError());
+#endif
+  } else {
+    BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_ic_kernel, dim3(G), dim3(IC_THREADS), args, IC_SMEM, ctx->stream));
+  }
   return 0;
 }
 

@@ -26,6 +26,16 @@ __device__ __forceinline__ double pen_weight(const b200flow_penalty &pn, double 
   return 0.0;
 }
 
+// Same weights for the ASSEMBLY kernels.  The generalized Charbonnier weight 2a (s2 + x^2)^(a-1) is the only penalty that
+// needs a transcendental (nine of them per pixel in Classic+NL / classic++): pow() costs ~200 instructions (double-double
+// logarithm behind a call), exp((a-1) log y) ~70 inlined ones.  Relative error <= |(a-1) ln y| 2^-53 + 2 ulp < 2e-15
+// for y in [1e-12, 1e12] -- the operator tests hold the assembled A, b to 1e-11 relative, and the public
+// RobustFunction.deriv_over_x (pen_eval below) keeps pow().
+__device__ __forceinline__ double pen_weight_asm(const b200flow_penalty &pn, double x) {
+  if (pn.kind == 3) return 2.0 * pn.p1 * exp((pn.p1 - 1.0) * log(pn.p0 * pn.p0 + x * x));
+  return pen_weight(pn, x);
+}
+
 __device__ double pen_eval(const b200flow_penalty &pn, int d_type, double x, double tdist_const) {
   if (d_type == 2) return pen_weight(pn, x);
   double s2 = pn.p0 * pn.p0;
@@ -234,15 +244,21 @@ __device__ __forceinline__ bool warp_hermite(const double4 *__restrict__ s, int 
   double hx[2], gx[2], dhx[2], dgx[2], hy[2], gy[2], dhy[2], dgy[2];
   hermite_basis(ax, hx[0], hx[1], gx[0], gx[1], dhx[0], dhx[1], dgx[0], dgx[1]);
   hermite_basis(ay, hy[0], hy[1], gy[0], gy[1], dhy[0], dhy[1], dgy[0], dgy[1]);
+  // sum over the four corners of (hx, gx) (x) (hy, gy) against {Z, DX, DY, DXY}, factored: the x-direction products
+  // P, Q (value basis) and dP, dQ (derivative basis) are shared by val / ddx / ddy -- 14 fused multiply-adds per corner
+  // instead of 36 multiplies + 12 adds (the library is built with -fmad=false; these are explicit: the result is a
+  // smooth function of the inputs, no discrete decision depends on its last bit)
   val = ddx = ddy = 0.0;
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      double4 c = ld4(&s[(long long)(b ? yb : y0) * W + (a ? xb : x0)]);   // {Z, DX, DY, DXY}
-      val += c.x * hx[a] * hy[b] + c.y * gx[a] * hy[b] + c.z * hx[a] * gy[b] + c.w * gx[a] * gy[b];
-      ddx += c.x * dhx[a] * hy[b] + c.y * dgx[a] * hy[b] + c.z * dhx[a] * gy[b] + c.w * dgx[a] * gy[b];
-      ddy += c.x * hx[a] * dhy[b] + c.y * gx[a] * dhy[b] + c.z * hx[a] * dgy[b] + c.w * gx[a] * dgy[b];
+      const double4 c = ld4(&s[(long long)(b ? yb : y0) * W + (a ? xb : x0)]);   // {Z, DX, DY, DXY}
+      const double P = fma(c.y, gx[a], c.x * hx[a]), Q = fma(c.w, gx[a], c.z * hx[a]);
+      const double dP = fma(c.y, dgx[a], c.x * dhx[a]), dQ = fma(c.w, dgx[a], c.z * dhx[a]);
+      val = fma(P, hy[b], fma(Q, gy[b], val));
+      ddx = fma(dP, hy[b], fma(dQ, gy[b], ddx));
+      ddy = fma(P, dhy[b], fma(Q, dgy[b], ddy));
     }
   return true;
 }
@@ -318,16 +334,16 @@ __device__ __forceinline__ double blended_edge(const PenaltySet &ps, const b200f
                                                const b200flow_penalty &qua, double delta) {
   if (ps.hs) return ps.hs_w;
   double w = 0.0;
-  if (ps.alpha > 0.0) w = w + ps.alpha * (ps.lambda_q * pen_weight(qua, delta));
-  if (ps.alpha < 1.0) w = w + (1.0 - ps.alpha) * (ps.lambda * pen_weight(rob, delta));
+  if (ps.alpha > 0.0) w = w + ps.alpha * (ps.lambda_q * pen_weight_asm(qua, delta));
+  if (ps.alpha < 1.0) w = w + (1.0 - ps.alpha) * (ps.lambda * pen_weight_asm(rob, delta));
   return w;
 }
 
 __device__ __forceinline__ double blended_data(const PenaltySet &ps, double it_lin) {
   if (ps.hs) return ps.hs_d;
   double d = 0.0;
-  if (ps.alpha > 0.0) d = d + ps.alpha * pen_weight(ps.qua_d, it_lin);
-  if (ps.alpha < 1.0) d = d + (1.0 - ps.alpha) * pen_weight(ps.rho_d, it_lin);
+  if (ps.alpha > 0.0) d = d + ps.alpha * pen_weight_asm(ps.qua_d, it_lin);
+  if (ps.alpha < 1.0) d = d + (1.0 - ps.alpha) * pen_weight_asm(ps.rho_d, it_lin);
   return d;
 }
 
@@ -363,46 +379,73 @@ struct DataAccum {
   }
 };
 
+// One pixel of the assembled system.  Every edge weight is computed ONCE, by the pixel that stores it (its right and
+// down edges), and handed to the neighbour on the other side through shared memory (sH / sV, the CTA's 32 x 8 tile);
+// only the tile's first column / row recompute their left / up edge (the weight is an even function of the flow
+// difference, so both sides get the same bits).  8 -> 4.3 penalty evaluations per pixel.  Must be called by every thread
+// of the CTA (`in` = the thread has a pixel); SHARE = false is the plain per-pixel form for callers without a tile.
+template <bool SHARE>
 __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const double2 *__restrict__ uv,
-                                               const double2 *__restrict__ duv, int H, int W, int x, int y, DataTerm dt,
-                                               const LinSys &sys, long long gi) {
-  long long i = (long long)y * W + x;
-  double2 c0 = uv[i];                                       // uv (for the rhs Laplacian)
-  double2 dc = duv ? duv[i] : make_double2(0.0, 0.0);
-  double2 c = make_double2(c0.x + dc.x, c0.y + dc.y);       // uv + duv (for the weights)
+                                               const double2 *__restrict__ duv, int H, int W, int x, int y, bool in,
+                                               DataTerm dt, const LinSys &sys, long long gi, double2 (*sH)[32],
+                                               double2 (*sV)[32]) {
+  const long long i = (long long)y * W + x;
+  double2 c0 = make_double2(0.0, 0.0), c = c0;
   double whu = 0.0, whv = 0.0, wvu = 0.0, wvv = 0.0;        // own right / down edges (stored)
-  double lu = 0.0, lv = 0.0;                                // sum_q w_pq (uv[p] - uv[q])
+  double lr_u = 0.0, lr_v = 0.0, ld_u = 0.0, ld_v = 0.0;    // w (uv[p] - uv[q]) of the right / down edge
   auto nb = [&](long long j, double2 &n0, double2 &n) {
     n0 = uv[j];
     double2 nd = duv ? duv[j] : make_double2(0.0, 0.0);
     n = make_double2(n0.x + nd.x, n0.y + nd.y);
   };
   double2 n0, n;
-  if (x + 1 < W) {   // right: delta = f[x+1] - f[x]
-    nb(i + 1, n0, n);
-    whu = blended_edge(ps, ps.rho_su[0], ps.qua_su[0], n.x - c.x);
-    whv = blended_edge(ps, ps.rho_sv[0], ps.qua_sv[0], n.y - c.y);
-    lu += whu * (c0.x - n0.x);
-    lv += whv * (c0.y - n0.y);
+  if (in) {
+    c0 = uv[i];                                             // uv (for the rhs Laplacian)
+    const double2 dc = duv ? duv[i] : make_double2(0.0, 0.0);
+    c = make_double2(c0.x + dc.x, c0.y + dc.y);             // uv + duv (for the weights)
+    if (x + 1 < W) {   // right: delta = f[x+1] - f[x]
+      nb(i + 1, n0, n);
+      whu = blended_edge(ps, ps.rho_su[0], ps.qua_su[0], n.x - c.x);
+      whv = blended_edge(ps, ps.rho_sv[0], ps.qua_sv[0], n.y - c.y);
+      lr_u = whu * (c0.x - n0.x);
+      lr_v = whv * (c0.y - n0.y);
+    }
+    if (y + 1 < H) {   // down
+      nb(i + W, n0, n);
+      wvu = blended_edge(ps, ps.rho_su[1], ps.qua_su[1], n.x - c.x);
+      wvv = blended_edge(ps, ps.rho_sv[1], ps.qua_sv[1], n.y - c.y);
+      ld_u = wvu * (c0.x - n0.x);
+      ld_v = wvv * (c0.y - n0.y);
+    }
   }
+  if (SHARE) {
+    sH[threadIdx.y][threadIdx.x] = make_double2(whu, whv);
+    sV[threadIdx.y][threadIdx.x] = make_double2(wvu, wvv);
+    __syncthreads();
+  }
+  if (!in) return;
+  double lu = 0.0, lv = 0.0;                                // sum_q w_pq (uv[p] - uv[q]) in the order right, left, down, up
+  lu += lr_u; lv += lr_v;
   if (x > 0) {       // left edge belongs to pixel x-1: delta = f[x] - f[x-1]
     nb(i - 1, n0, n);
-    double wu = blended_edge(ps, ps.rho_su[0], ps.qua_su[0], c.x - n.x);
-    double wv = blended_edge(ps, ps.rho_sv[0], ps.qua_sv[0], c.y - n.y);
+    double wu, wv;
+    if (SHARE && threadIdx.x > 0) { const double2 e = sH[threadIdx.y][threadIdx.x - 1]; wu = e.x; wv = e.y; }
+    else {
+      wu = blended_edge(ps, ps.rho_su[0], ps.qua_su[0], c.x - n.x);
+      wv = blended_edge(ps, ps.rho_sv[0], ps.qua_sv[0], c.y - n.y);
+    }
     lu += wu * (c0.x - n0.x);
     lv += wv * (c0.y - n0.y);
   }
-  if (y + 1 < H) {   // down
-    nb(i + W, n0, n);
-    wvu = blended_edge(ps, ps.rho_su[1], ps.qua_su[1], n.x - c.x);
-    wvv = blended_edge(ps, ps.rho_sv[1], ps.qua_sv[1], n.y - c.y);
-    lu += wvu * (c0.x - n0.x);
-    lv += wvv * (c0.y - n0.y);
-  }
+  lu += ld_u; lv += ld_v;
   if (y > 0) {       // up
     nb(i - W, n0, n);
-    double wu = blended_edge(ps, ps.rho_su[1], ps.qua_su[1], c.x - n.x);
-    double wv = blended_edge(ps, ps.rho_sv[1], ps.qua_sv[1], c.y - n.y);
+    double wu, wv;
+    if (SHARE && threadIdx.y > 0) { const double2 e = sV[threadIdx.y - 1][threadIdx.x]; wu = e.x; wv = e.y; }
+    else {
+      wu = blended_edge(ps, ps.rho_su[1], ps.qua_su[1], c.x - n.x);
+      wv = blended_edge(ps, ps.rho_sv[1], ps.qua_sv[1], c.y - n.y);
+    }
     lu += wu * (c0.x - n0.x);
     lv += wv * (c0.y - n0.y);
   }
@@ -422,61 +465,69 @@ __global__ void __launch_bounds__(256, MULTI ? 1 : 3) warp_assemble_kernel(const
                                      const double2 *__restrict__ uv, const double2 *__restrict__ duv, int H, int W,
                                      int interp, double blend, PenaltySet ps, LinSys sys, double *__restrict__ It,
                                      double *__restrict__ Ix, double *__restrict__ Iy, int do_assemble) {
+  __shared__ double2 sH[8][32], sV[8][32];                 // the tile's right / down edge weights (assemble_pixel)
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= W || y >= H) return;
+  const bool in = x < W && y < H;
+  if (!in && !do_assemble) return;
   const long long HW = (long long)H * W;
   long long off = (long long)blockIdx.z * HW;
   long long i = (long long)y * W + x;
-  const double2 f = uv[off + i];
-  const double2 dc = duv ? duv[off + i] : make_double2(0.0, 0.0);
-  DataTerm dt;
-  if (!MULTI) {
-    Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride, I1x + off, I1y + off, src2 + off, H, W, x, y, f,
-                           interp, blend);
-    if (It) { It[off + i] = dv.It; Ix[off + i] = dv.Ix; Iy[off + i] = dv.Iy; }
-    dt = data_term_single(ps, dv, dc);
-  } else {
-    DataAccum acc;
-    for (int c = 0; c < NC; ++c) {
-      const long long coff = ((long long)blockIdx.z * NC + c) * HW;
-      Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride + (long long)c * HW, I1x + coff, I1y + coff,
-                             src2 + coff, H, W, x, y, f, interp, blend);
-      if (It) { It[coff + i] = dv.It; Ix[coff + i] = dv.Ix; Iy[coff + i] = dv.Iy; }
-      acc.add(ps, dv, dc);
+  DataTerm dt = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (in) {
+    const double2 f = uv[off + i];
+    const double2 dc = duv ? duv[off + i] : make_double2(0.0, 0.0);
+    if (!MULTI) {
+      Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride, I1x + off, I1y + off, src2 + off, H, W, x, y, f,
+                             interp, blend);
+      if (It) { It[off + i] = dv.It; Ix[off + i] = dv.Ix; Iy[off + i] = dv.Iy; }
+      dt = data_term_single(ps, dv, dc);
+    } else {
+      DataAccum acc;
+      for (int c = 0; c < NC; ++c) {
+        const long long coff = ((long long)blockIdx.z * NC + c) * HW;
+        Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride + (long long)c * HW, I1x + coff, I1y + coff,
+                               src2 + coff, H, W, x, y, f, interp, blend);
+        if (It) { It[coff + i] = dv.It; Ix[coff + i] = dv.Ix; Iy[coff + i] = dv.Iy; }
+        acc.add(ps, dv, dc);
+      }
+      dt = acc.finish(NC);
     }
-    dt = acc.finish(NC);
   }
-  if (do_assemble) assemble_pixel(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, dt, sys, off + i);
+  if (do_assemble)
+    assemble_pixel<true>(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, in, dt, sys, off + i, sH, sV);
 }
 
 // It, Ix, Iy: [B][NC][H][W]
 __global__ void __launch_bounds__(256, 3) assemble_from_deriv_kernel(const double *__restrict__ It, const double *__restrict__ Ix,
                                            const double *__restrict__ Iy, int NC, const double2 *__restrict__ uv,
                                            const double2 *__restrict__ duv, int H, int W, PenaltySet ps, LinSys sys) {
+  __shared__ double2 sH[8][32], sV[8][32];
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= W || y >= H) return;
+  const bool in = x < W && y < H;
   const long long HW = (long long)H * W;
   long long off = (long long)blockIdx.z * HW;
   long long i = (long long)y * W + x;
-  const double2 dc = duv ? duv[off + i] : make_double2(0.0, 0.0);
-  DataTerm dt;
-  if (NC == 1) {
-    Deriv dv;
-    dv.It = It[off + i]; dv.Ix = Ix[off + i]; dv.Iy = Iy[off + i];
-    dt = data_term_single(ps, dv, dc);
-  } else {
-    DataAccum acc;
-    for (int c = 0; c < NC; ++c) {
-      const long long j = ((long long)blockIdx.z * NC + c) * HW + i;
+  DataTerm dt = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (in) {
+    const double2 dc = duv ? duv[off + i] : make_double2(0.0, 0.0);
+    if (NC == 1) {
       Deriv dv;
-      dv.It = It[j]; dv.Ix = Ix[j]; dv.Iy = Iy[j];
-      acc.add(ps, dv, dc);
+      dv.It = It[off + i]; dv.Ix = Ix[off + i]; dv.Iy = Iy[off + i];
+      dt = data_term_single(ps, dv, dc);
+    } else {
+      DataAccum acc;
+      for (int c = 0; c < NC; ++c) {
+        const long long j = ((long long)blockIdx.z * NC + c) * HW + i;
+        Deriv dv;
+        dv.It = It[j]; dv.Ix = Ix[j]; dv.Iy = Iy[j];
+        acc.add(ps, dv, dc);
+      }
+      dt = acc.finish(NC);
     }
-    dt = acc.finish(NC);
   }
-  assemble_pixel(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, dt, sys, off + i);
+  assemble_pixel<true>(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, in, dt, sys, off + i, sH, sV);
 }
 
 int k_warp_assemble(b200flow_ctx *ctx, const double *frames, long long bstride, int NC, const double *I1x, const double *I1y,

@@ -90,6 +90,7 @@ _SIGS = {
 }
 _SIGS["b200flow_host_alloc"] = [C.c_ulonglong, C.POINTER(_vp)]
 _SIGS["b200flow_host_free"] = [_vp]
+_SIGS["b200flow_ctx_set_split"] = [C.c_int, C.c_int]
 
 EXPORTS = sorted(list(_SIGS) + ["b200flow_abi_version", "b200flow_ctx_create", "b200flow_ctx_destroy",
                                 "b200flow_last_error", "b200flow_ctx_set_timing", "b200flow_ctx_sync",
@@ -173,6 +174,10 @@ class Context:
 
     def sync(self):
         self.lib.b200flow_ctx_sync(self.handle)
+
+    def set_split(self, groups, solver_ctas_per_sm=0):
+        """Concurrent sub-batches: batched calls run `groups` groups of pairs on their own streams (include/b200flow.h)."""
+        self.call("b200flow_ctx_set_split", int(groups), int(solver_ctas_per_sm))
 
     @property
     def stream(self):

@@ -260,8 +260,14 @@ class BaseOpticalFlow(ABC):
         Cn = 0
         if color is not None:
             color = _lib.f64(color)
+            # the library reads H*W*C values: a guidance image of another size would be read past its end.  The reference
+            # resizes it with skimage (weighted_median.py:49-56); skimage is not a dependency here, so say so instead.
+            if color.ndim not in (2, 3) or color.shape[:2] != (H, W):
+                raise ValueError("color_images must be (%d, %d) or (%d, %d, C); got %s" % (H, W, H, W, color.shape))
             Cn = 1 if color.ndim == 2 else color.shape[2]
         init = None if init is None else _lib.f64(init)
+        if init is not None and init.shape != (H, W, 2):
+            raise ValueError("init must be (%d, %d, 2); got %s" % (H, W, init.shape))
         uv = np.empty((H, W, 2))
         st = _lib.Stats()
         ctx = _lib.default_context()
