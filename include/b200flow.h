@@ -30,7 +30,7 @@ extern "C" {
 #define B200FLOW_ECUDA   (-2)
 #define B200FLOW_ENOCONV (-3)
 
-#define B200FLOW_ABI_VERSION 1
+#define B200FLOW_ABI_VERSION 2
 
 typedef struct b200flow_ctx b200flow_ctx;
 
@@ -80,6 +80,20 @@ typedef struct {
   int final_median;           /* HS: median once more after the finest level (hs.py:95-97) */
 } b200flow_params;
 
+/* kernel groups of the pipeline, in the order of DESIGN.md section 4 */
+enum { B200FLOW_K_ROF = 0,        /* structure-texture decomposition (image_processing.py:52-136) or scale_image */
+       B200FLOW_K_PYRAMID = 1,    /* Gaussian pyramids (pyramid.py:44-73) */
+       B200FLOW_K_RESAMPLE = 2,   /* resample_flow (warping.py:6-45) */
+       B200FLOW_K_LEVEL_PREP = 3, /* per-level derivative planes + spline prefilter (derivatives.py:201-259) */
+       B200FLOW_K_WARP_ASSEMBLE = 4, /* partial_deriv + IRLS weights + flow_operator, fused */
+       B200FLOW_K_SOLVER = 5,     /* _solve_linear_system (base.py:87-172) */
+       B200FLOW_K_CLIP_ADD = 6,   /* update step clip / add (classic_nl.py:255-262) */
+       B200FLOW_K_OCCLUSION = 7,  /* detect_occlusion (occlusion.py:6-56) */
+       B200FLOW_K_WMEDIAN = 8,    /* denoise_color_weighted_medfilt2 (weighted_median.py:24-112) */
+       B200FLOW_K_MEDIAN = 9,     /* median_filter call sites */
+       B200FLOW_K_MISC = 10,      /* norm gate, duv differences, copies */
+       B200FLOW_K_COUNT = 11 };
+
 /* per-call statistics of b200flow_estimate*, optional (may be NULL) */
 typedef struct {
   int solves;                 /* linear solves performed (per batch, not per pair) */
@@ -88,6 +102,12 @@ typedef struct {
   int kernel_launches;        /* CUDA kernels launched by this call */
   int not_converged;          /* solves that stopped at maxit */
   double solver_ms, warp_ms, filter_ms, pre_ms, total_ms;  /* CUDA-event times on the ctx stream (0 unless timing enabled) */
+  /* per kernel group (B200FLOW_K_*): CUDA-event time (0 unless timing enabled), ALGORITHMIC bytes moved (DESIGN.md
+   * section 4: the per-pixel figure x the pixels of every launch; always filled) and launches.  With concurrent
+   * sub-batches kernel_ms is the time during which at least one group was inside that kernel group. */
+  double kernel_ms[B200FLOW_K_COUNT];
+  double kernel_bytes[B200FLOW_K_COUNT];
+  int kernel_calls[B200FLOW_K_COUNT];
 } b200flow_stats;
 
 int  b200flow_abi_version(void);

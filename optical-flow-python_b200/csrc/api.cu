@@ -71,6 +71,9 @@ void b200flow_ctx_destroy(b200flow_ctx *ctx) {
     cudaStreamSynchronize(c->stream);
     for (auto &k : c->chunks) cudaFree(k.base);
     cudaStreamDestroy(c->stream);
+    if (c->solver_stream) cudaStreamDestroy(c->solver_stream);
+    if (c->ev_s0) cudaEventDestroy(c->ev_s0);
+    if (c->ev_s1) cudaEventDestroy(c->ev_s1);
     delete c;
   }
   for (auto e : ctx->ev_join) cudaEventDestroy(e);

@@ -35,6 +35,9 @@ struct b200flow_ctx {
   int nsplit = 1;
   int solver_ctas_per_sm = 0;       // 0 = all the runtime allows
   bool plain_solver_launch = false; // children of a split context: <<<>>> instead of cudaLaunchCooperativeKernel
+  cudaStream_t solver_stream = nullptr;   // children only: high-priority stream the persistent solver is launched on, so
+                                          // that its CTAs are dispatched ahead of a sibling's pending weighted-median CTAs
+  cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
   b200flow_ctx *parent = nullptr;
   std::vector<b200flow_ctx *> subs; // child contexts (own stream + arena), created on demand
   cudaEvent_t ev_fork = nullptr;

@@ -55,7 +55,11 @@ struct StageTimer {
   ~StageTimer() { clear(); }
   StageTimer(const StageTimer &) = delete;
   StageTimer &operator=(const StageTimer &) = delete;
-  void begin(int cat) {
+  double bytes[B200FLOW_K_COUNT] = {0};   // algorithmic bytes per kernel group (always accumulated)
+  int calls[B200FLOW_K_COUNT] = {0};
+  void begin(int cat, double nbytes = 0.0) {
+    bytes[cat] += nbytes;
+    calls[cat] += 1;
     if (!on) return;
     Span s;
     cudaEventCreate(&s.a);
@@ -82,9 +86,13 @@ struct StageTimer {
   }
 };
 // total length of the union of the intervals of one category (ms)
-static double union_ms(std::vector<Interval> v, int cat) {
+static double union_ms(const std::vector<Interval> &v, const int *cats) {
   std::vector<std::pair<float, float>> w;
-  for (auto &i : v) if (i.cat == cat && i.b > i.a) w.push_back({i.a, i.b});
+  for (auto &i : v) {
+    bool take = false;
+    for (const int *c = cats; *c >= 0; ++c) take |= i.cat == *c;
+    if (take && i.b > i.a) w.push_back({i.a, i.b});
+  }
   std::sort(w.begin(), w.end());
   double total = 0.0;
   float ca = 0.f, cb = -1.f;
@@ -95,7 +103,11 @@ static double union_ms(std::vector<Interval> v, int cat) {
   if (cb > ca) total += cb - ca;
   return total;
 }
-enum { T_PRE = 0, T_WARP = 1, T_SOLVE = 2, T_FILTER = 3 };
+// the four coarse stages reported since round 1, as unions of kernel groups
+static const int STAGE_PRE[] = {B200FLOW_K_ROF, B200FLOW_K_PYRAMID, -1};
+static const int STAGE_WARP[] = {B200FLOW_K_RESAMPLE, B200FLOW_K_LEVEL_PREP, B200FLOW_K_WARP_ASSEMBLE, -1};
+static const int STAGE_SOLVE[] = {B200FLOW_K_SOLVER, -1};
+static const int STAGE_FILTER[] = {B200FLOW_K_CLIP_ADD, B200FLOW_K_OCCLUSION, B200FLOW_K_WMEDIAN, B200FLOW_K_MEDIAN, B200FLOW_K_MISC, -1};
 
 int check_params(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int W, int C) {
   if (!p) return set_err(ctx, B200FLOW_EINVAL, "params is NULL");
@@ -149,7 +161,7 @@ struct PipelineRun {
   StageTimer tm;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long *dstats = nullptr;
-  int solves = 0, launches0 = 0;
+  int solves = 0, launches0 = 0, solver_bytes = 0;
   PipelineRun() {}
   PipelineRun(const PipelineRun &) = delete;
   PipelineRun &operator=(const PipelineRun &) = delete;
@@ -161,10 +173,22 @@ struct PipelineRun {
 
 struct RunResult {
   long long hstats[4] = {0, 0, 0, 0};
-  std::vector<Interval> iv;       // stage spans relative to the base event (ms)
+  std::vector<Interval> iv;       // kernel-group spans relative to the base event (ms)
+  double bytes[B200FLOW_K_COUNT] = {0};
+  int calls[B200FLOW_K_COUNT] = {0};
+  int solver_bytes_per_pixel_iter = 0;
   float t0 = 0.f, t1 = 0.f;       // begin / end of the run relative to the base event
   int solves = 0, launches = 0;
 };
+
+// one kernel-group call under the stage timer (events only when ctx->timing; bytes and calls always)
+#define TIMED(K, nbytes, call)       \
+  do {                               \
+    tm.begin((K), (nbytes));         \
+    int rc_t_ = (call);              \
+    tm.end();                        \
+    if (rc_t_ < 0) return rc_t_;     \
+  } while (0)
 
 // Queues the whole coarse-to-fine loop of B pairs on ctx->stream; never synchronises (unless B200FLOW_TRACE is set).
 // gray_planar: [B][2*NC][H][W] -- NC channels of frame 1, then NC channels of frame 2 (NC = 1 for gray frames)
@@ -188,20 +212,22 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
   }
 
   // ---- pre-processing: texture or [0,255] scaling (joint over the two frames of a pair) ----
-  tm.begin(T_PRE);
   double *pre;
   BF_TRY(arena_alloc(ctx, &pre, NP * N));
   // Horn-Schunck calls structure_texture_decomposition_rof(self.images) with the function's own defaults
   // (hs.py:66-67: theta 1/8, 100 iterations, alp 0.95), whatever self.alp says; BA / Classic+NL pass self.alp
+  const int rof_iters = hs ? 100 : p->rof_iters;
+  tm.begin(B200FLOW_K_ROF, p->texture > 0 ? (40.0 * rof_iters + 32.0) * NP * N : 32.0 * NP * N);
   if (p->texture > 0)
-    BF_TRY(k_rof_texture(ctx, gray_planar, pre, B, NP, H, W, hs ? 1.0 / 8 : p->rof_theta, hs ? 100 : p->rof_iters,
-                         hs ? 0.95 : p->alp));
+    BF_TRY(k_rof_texture(ctx, gray_planar, pre, B, NP, H, W, hs ? 1.0 / 8 : p->rof_theta, rof_iters, hs ? 0.95 : p->alp));
   else if (p->texture == 0) BF_TRY(k_minmax_scale(ctx, gray_planar, pre, B, NP * HW, 0.0, 255.0));
   else BF_CUDA(ctx, cudaMemcpyAsync(pre, gray_planar, NP * N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  tm.end();
 
   int levels = (hs || p->auto_level) ? auto_levels(H, W, p->pyramid_spacing) : p->pyramid_levels;
   if (p->pyramid_levels > 0 && !p->auto_level) levels = p->pyramid_levels;
   Pyramid pyr, gpyr, cpyr, gcpyr;
+  tm.begin(B200FLOW_K_PYRAMID);
   BF_TRY(build_pyramid(ctx, pre, NP * B, H, W, levels, p->pyramid_spacing, &pyr));
   const bool use_color = cnl && color_planar != nullptr && C > 0;
   if (!hs) {
@@ -213,6 +239,13 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
     }
   }
   tm.end();
+  {  // pyramid: every level reads its source level once and writes itself once (8 B per plane pixel each)
+    const Pyramid *all[4] = {&pyr, &gpyr, &cpyr, &gcpyr};
+    const int planes[4] = {NP * B, NP * B, C * B, C * B};
+    for (int k = 0; k < 4; ++k)
+      for (size_t l = 1; l < all[k]->lv.size(); ++l)
+        tm.bytes[B200FLOW_K_PYRAMID] += 8.0 * planes[k] * ((double)all[k]->H[l - 1] * all[k]->W[l - 1] + (double)all[k]->H[l] * all[k]->W[l]);
+  }
 
   // ---- work buffers at full resolution, reused by every level ----
   double2 *uvA, *uvB, *x, *cand = nullptr, *duv = nullptr;
@@ -270,12 +303,13 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
       const long long hw = (long long)h * w;
       const double *frames = ip.lv[l];
       const long long bstride = NP * hw;
-      tm.begin(T_WARP);
-      BF_TRY(k_resample_flow(ctx, cur, nxt, B, ch, cw, h, w));
+      const double npx = (double)B * hw;   // pixels of this level over the batch: the unit of the per-pixel byte figures
+      TIMED(B200FLOW_K_RESAMPLE, 16.0 * B * ((double)ch * cw + (double)hw), k_resample_flow(ctx, cur, nxt, B, ch, cw, h, w));
       std::swap(cur, nxt);
       ch = h; cw = w;
-      BF_TRY(k_level_prep(ctx, frames, bstride, B, NC, h, w, p->interp, p->deriv_filter, I1x, I1y, src2));
-      tm.end();
+      // Hermite: read im1, im2 16, write I1x, I1y 16 + {Z, DX, DY, DXY} 32; spline: + two in-place prefilter passes of 32 B r/w
+      TIMED(B200FLOW_K_LEVEL_PREP, (p->interp == B200FLOW_INTERP_CUBIC ? 64.0 + 128.0 : 64.0) * NC * npx,
+            k_level_prep(ctx, frames, bstride, B, NC, h, w, p->interp, p->deriv_filter, I1x, I1y, src2));
       sys.H = h; sys.W = w;
       if (hs) BF_LAUNCH(ctx, fill_int_kernel, (unsigned)cdiv(B, 128), 128, 0, active, B, 1);
       const int warps = hs ? p->max_warping_iters : p->max_iters;
@@ -284,16 +318,27 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
       for (int it = 0; it < warps; ++it) {
         const double2 *dcur = nullptr;    // duv of the current linearisation (zero on the first pass)
         for (int j = 0; j < nlin; ++j) {
-          tm.begin(T_WARP);
           if (j == 0)
-            BF_TRY(k_warp_assemble(ctx, frames, bstride, NC, I1x, I1y, src2, cur, nullptr, B, h, w, p->interp, p->blend, ps,
-                                   sys, nlin > 1 ? It : nullptr, Ix, Iy));
+            TIMED(B200FLOW_K_WARP_ASSEMBLE, (88.0 + 56.0 * NC) * npx,
+                  k_warp_assemble(ctx, frames, bstride, NC, I1x, I1y, src2, cur, nullptr, B, h, w, p->interp, p->blend, ps,
+                                  sys, nlin > 1 ? It : nullptr, Ix, Iy));
           else
-            BF_TRY(k_assemble_from_deriv(ctx, It, Ix, Iy, NC, cur, dcur, B, h, w, ps, sys));
+            TIMED(B200FLOW_K_WARP_ASSEMBLE, (104.0 + 24.0 * NC) * npx,
+                  k_assemble_from_deriv(ctx, It, Ix, Iy, NC, cur, dcur, B, h, w, ps, sys));
+          if (ctx->solver_stream) {          // concurrent sub-batches: the solver runs on the group's high-priority stream
+            BF_CUDA(ctx, cudaEventRecord(ctx->ev_s0, ctx->stream));
+            BF_CUDA(ctx, cudaStreamWaitEvent(ctx->solver_stream, ctx->ev_s0, 0));
+            std::swap(ctx->stream, ctx->solver_stream);
+          }
+          tm.begin(B200FLOW_K_SOLVER);       // its bytes = pixel-iterations (device counter) x bytes per pixel-iteration
+          int rc_solve = k_pcg_solve_async(ctx, sys, work, x, p->tol, p->maxit, pcg_mode, dstats);
           tm.end();
-          tm.begin(T_SOLVE);
-          BF_TRY(k_pcg_solve_async(ctx, sys, work, x, p->tol, p->maxit, pcg_mode, dstats));
-          tm.end();
+          if (ctx->solver_stream) {
+            std::swap(ctx->stream, ctx->solver_stream);
+            BF_CUDA(ctx, cudaEventRecord(ctx->ev_s1, ctx->solver_stream));
+            BF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_s1, 0));
+          }
+          BF_TRY(rc_solve);
           if (trace) {   // B200FLOW_TRACE=1 (debug): per-solve time and per-system iteration counts; synchronises
             std::vector<int> fl(1 + 2 * B);
             cudaMemcpyAsync(fl.data(), work.flags, sizeof(int) * fl.size(), cudaMemcpyDeviceToHost, ctx->stream);
@@ -307,33 +352,36 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
                     mx ? 1e3 * ms / mx : 0.0, ms > 0 ? (double)sum * hw * pcg_bytes_per_pixel_iter(pcg_mode) / (ms * 1e6) : 0.0);
           }
           solves++;
-          tm.begin(T_FILTER);
+          const double median_bytes = 32.0 * npx, clip_bytes = 48.0 * npx;
           if (hs) {
-            BF_TRY(k_hs_norm_gate(ctx, x, B, hw, active, nscratch));
+            TIMED(B200FLOW_K_MISC, 16.0 * npx, k_hs_norm_gate(ctx, x, B, hw, active, nscratch));
             if (have_median && p->mf_iter >= 1) {     // hs.py:137-140: mf_iter passes, none at all when mf_iter < 1
-              BF_TRY(k_median_uv(ctx, cur, x, p->limit_update, active, nxt, B, h, w, mh, mw, 1));
+              TIMED(B200FLOW_K_MEDIAN, median_bytes + 16.0 * npx,
+                    k_median_uv(ctx, cur, x, p->limit_update, active, nxt, B, h, w, mh, mw, 1));
               for (int m = 1; m < p->mf_iter; ++m) {
                 std::swap(cur, nxt);
-                BF_TRY(k_median_uv(ctx, cur, nullptr, 0, active, nxt, B, h, w, mh, mw, 1));
+                TIMED(B200FLOW_K_MEDIAN, median_bytes, k_median_uv(ctx, cur, nullptr, 0, active, nxt, B, h, w, mh, mw, 1));
               }
             } else {
-              BF_TRY(k_clip_add(ctx, cur, x, p->limit_update, active, nxt, hw, B));
+              TIMED(B200FLOW_K_CLIP_ADD, clip_bytes, k_clip_add(ctx, cur, x, p->limit_update, active, nxt, hw, B));
             }
           } else if (cnl && have_median && use_color) {
-            BF_TRY(k_clip_add(ctx, cur, x, p->limit_update, nullptr, cand, hw, B));
-            BF_TRY(k_occlusion(ctx, cand, frames, bstride, NC, B, h, w, p->occ_sigma_d, p->occ_sigma_i, occ));
-            BF_TRY(k_weighted_median(ctx, cand, cur, cp.lv[l], C, occ, B, h, w, p->area_hsz, p->sigma_i, nxt));
+            TIMED(B200FLOW_K_CLIP_ADD, clip_bytes, k_clip_add(ctx, cur, x, p->limit_update, nullptr, cand, hw, B));
+            TIMED(B200FLOW_K_OCCLUSION, (24.0 + 16.0 * NC) * npx,
+                  k_occlusion(ctx, cand, frames, bstride, NC, B, h, w, p->occ_sigma_d, p->occ_sigma_i, occ));
+            TIMED(B200FLOW_K_WMEDIAN, (56.0 + 8.0 * C) * npx,
+                  k_weighted_median(ctx, cand, cur, cp.lv[l], C, occ, B, h, w, p->area_hsz, p->sigma_i, nxt));
           } else if (have_median) {
             // BA (ba.py:197-201) and Classic+NL without a usable colour image (weighted_median.py:42-47: square mfsz[0])
-            BF_TRY(k_median_uv(ctx, cur, x, p->limit_update, nullptr, nxt, B, h, w, mh, cnl ? mh : mw, 0));
+            TIMED(B200FLOW_K_MEDIAN, median_bytes + 16.0 * npx,
+                  k_median_uv(ctx, cur, x, p->limit_update, nullptr, nxt, B, h, w, mh, cnl ? mh : mw, 0));
           } else {
-            BF_TRY(k_clip_add(ctx, cur, x, p->limit_update, nullptr, nxt, hw, B));
+            TIMED(B200FLOW_K_CLIP_ADD, clip_bytes, k_clip_add(ctx, cur, x, p->limit_update, nullptr, nxt, hw, B));
           }
           if (j + 1 < nlin) {               // next linearisation pass sees duv = filtered - uv
-            BF_TRY(k_sub(ctx, nxt, cur, duv, (long long)B * hw));
+            TIMED(B200FLOW_K_MISC, 48.0 * npx, k_sub(ctx, nxt, cur, duv, (long long)B * hw));
             dcur = duv;
           }
-          tm.end();
         }
         std::swap(cur, nxt);                 // uv = uv + duv
       }
@@ -349,15 +397,14 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
     return set_err(ctx, B200FLOW_EINVAL, "internal: final flow size %dx%d != %dx%d", ch, cw, H, W);
   }
   if (hs && have_median && p->final_median) {   // final median (hs.py:95-97)
-    tm.begin(T_FILTER);
-    BF_TRY(k_median_uv(ctx, cur, nullptr, 0, nullptr, nxt, B, H, W, mh, mw, 1));
-    tm.end();
+    TIMED(B200FLOW_K_MEDIAN, 32.0 * N, k_median_uv(ctx, cur, nullptr, 0, nullptr, nxt, B, H, W, mh, mw, 1));
     std::swap(cur, nxt);
   }
   BF_CUDA(ctx, cudaMemcpyAsync(uv_out, cur, N * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
   if (ctx->timing) cudaEventRecord(run->ev1, ctx->stream);
   run->dstats = dstats;
   run->solves = solves;
+  run->solver_bytes = pcg_bytes_per_pixel_iter(pcg_mode);
   return 0;
 }
 
@@ -365,6 +412,8 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
 static int pipeline_finish(b200flow_ctx *ctx, PipelineRun *run, bool want, cudaEvent_t base, RunResult *res) {
   res->solves = run->solves;
   res->launches = ctx->launches - run->launches0;
+  res->solver_bytes_per_pixel_iter = run->solver_bytes;
+  for (int k = 0; k < B200FLOW_K_COUNT; ++k) { res->bytes[k] = run->tm.bytes[k]; res->calls[k] = run->tm.calls[k]; }
   if (want || ctx->timing) {
     BF_CUDA(ctx, cudaMemcpyAsync(res->hstats, run->dstats, sizeof res->hstats, cudaMemcpyDeviceToHost, ctx->stream));
     BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -397,8 +446,17 @@ static void fill_stats(b200flow_stats *stats, const std::vector<RunResult> &rr, 
   }
   // with concurrent groups the spans of one category overlap in time: report the time during which at least one group
   // was in that stage (for one group this is the plain sum)
-  stats->pre_ms = union_ms(all, T_PRE); stats->warp_ms = union_ms(all, T_WARP);
-  stats->solver_ms = union_ms(all, T_SOLVE); stats->filter_ms = union_ms(all, T_FILTER);
+  stats->pre_ms = union_ms(all, STAGE_PRE); stats->warp_ms = union_ms(all, STAGE_WARP);
+  stats->solver_ms = union_ms(all, STAGE_SOLVE); stats->filter_ms = union_ms(all, STAGE_FILTER);
+  for (int k = 0; k < B200FLOW_K_COUNT; ++k) {
+    const int one[2] = {k, -1};
+    stats->kernel_ms[k] = union_ms(all, one);
+    stats->kernel_bytes[k] = 0.0;
+    stats->kernel_calls[k] = 0;
+    for (auto &r : rr) { stats->kernel_bytes[k] += r.bytes[k]; stats->kernel_calls[k] += r.calls[k]; }
+  }
+  stats->kernel_bytes[B200FLOW_K_SOLVER] = 0.0;
+  for (auto &r : rr) stats->kernel_bytes[B200FLOW_K_SOLVER] += (double)r.hstats[3] * r.solver_bytes_per_pixel_iter;
   stats->total_ms = timing ? (double)(t1 - t0) : 0.0;
 }
 
@@ -409,7 +467,13 @@ static int ensure_subs(b200flow_ctx *ctx, int ns) {
     c->device = ctx->device;
     c->num_sms = ctx->num_sms;
     c->parent = ctx;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    int pri_lo = 0, pri_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&pri_lo, &pri_hi);      // numerically lower = higher priority
+    const bool prio = getenv("B200FLOW_NO_SOLVER_PRIORITY") == nullptr;
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pri_lo) != cudaSuccess ||
+        (prio && (cudaStreamCreateWithPriority(&c->solver_stream, cudaStreamNonBlocking, pri_hi) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&c->ev_s0, cudaEventDisableTiming) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&c->ev_s1, cudaEventDisableTiming) != cudaSuccess))) {
       delete c;
       return set_err(ctx, B200FLOW_ECUDA, "cudaStreamCreate for a sub-batch failed");
     }

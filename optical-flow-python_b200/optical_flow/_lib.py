@@ -45,10 +45,17 @@ class Stats(C.Structure):
     _fields_ = [("solves", C.c_int), ("pcg_iters", C.c_longlong), ("pcg_pixel_iters", C.c_longlong),
                 ("kernel_launches", C.c_int), ("not_converged", C.c_int),
                 ("solver_ms", C.c_double), ("warp_ms", C.c_double), ("filter_ms", C.c_double),
-                ("pre_ms", C.c_double), ("total_ms", C.c_double)]
+                ("pre_ms", C.c_double), ("total_ms", C.c_double),
+                ("kernel_ms", C.c_double * 11), ("kernel_bytes", C.c_double * 11), ("kernel_calls", C.c_int * 11)]
+
+    KERNEL_GROUPS = ("rof", "pyramid", "resample_flow", "level_prep", "warp_assemble", "solver", "clip_add", "occlusion",
+                     "weighted_median", "median", "misc")
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("kernel_")}
+        d["kernels"] = {n: {"ms": self.kernel_ms[i], "bytes": self.kernel_bytes[i], "calls": self.kernel_calls[i]}
+                        for i, n in enumerate(self.KERNEL_GROUPS)}
+        return d
 
 
 _dp = C.POINTER(C.c_double)

@@ -5,19 +5,15 @@ O=gpurun_out
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
 $B --split 1 > $O/exp_split_1.json 2> $O/exp_split_1.err
 $B --split 2 > $O/exp_split_2.json 2> $O/exp_split_2.err
-B200FLOW_LIB=$PWD/optical-flow-python_b200/variants/lib_wm4.so $B --split 1 > $O/exp_split_1_wm4.json 2> $O/exp_split_1_wm4.err
+B200FLOW_NO_SOLVER_PRIORITY=1 $B --split 2 > $O/exp_split_2_noprio.json 2> $O/exp_split_2_noprio.err
 B200FLOW_LIB=$PWD/optical-flow-python_b200/variants/lib_wm4.so $B --split 2 > $O/exp_split_2_wm4.json 2> $O/exp_split_2_wm4.err
 $B --split 2 --batch 32 > $O/exp_split_2_b32.json 2> $O/exp_split_2_b32.err
-$B --split 1 --batch 32 > $O/exp_split_1_b32.json 2> $O/exp_split_1_b32.err
-B200FLOW_SOLVER_CTAS=1 python scripts/pcg_bench.py --solver 4 --cases 16,480,640 8,480,640 16,240,320 > $O/exp_pcgbench_1cta.log 2>&1
-python scripts/pcg_bench.py --solver 4 --cases 16,480,640 8,480,640 16,240,320 > $O/exp_pcgbench_2cta.log 2>&1
 for f in $O/exp_split_*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print({k:d[k] for k in ("value","ms_per_step","stage_ms_per_step","pcg_iters_per_step")}, d["e2e"]["value"], d["roofline"]["frac"])
+    print({k:d[k] for k in ("value","ms_per_step","stage_ms_per_step","pcg_iters_per_step")}, d["e2e"]["value"], d["roofline"]["frac"], d["roofline"]["measured"])
 except Exception as e:
     print("ERR", e, open(sys.argv[1].replace(".json",".err")).read()[-800:])
 PY
 done
-cat $O/exp_pcgbench_1cta.log $O/exp_pcgbench_2cta.log

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libb200flow.so does not export %s" % name
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.b200flow_abi_version() == 1
+    assert lib.b200flow_abi_version() == 2
 
 
 def test_params_struct_matches_header():
