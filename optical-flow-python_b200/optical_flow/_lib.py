@@ -52,7 +52,7 @@ class Stats(C.Structure):
                      "weighted_median", "median", "misc")
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("kernel_")}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("kernel_ms", "kernel_bytes", "kernel_calls")}
         d["kernels"] = {n: {"ms": self.kernel_ms[i], "bytes": self.kernel_bytes[i], "calls": self.kernel_calls[i]}
                         for i, n in enumerate(self.KERNEL_GROUPS)}
         return d

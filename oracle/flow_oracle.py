@@ -701,10 +701,14 @@ def detect_occlusion(uv, images, sigma_d=0.3, sigma_i=20.0):
     return np.exp(-div ** 2 / (2 * sigma_d ** 2)) * np.exp(-it ** 2 / (2 * sigma_i ** 2))
 
 
-def weighted_median_filter(uv, color, occ, hsz, sigma_i, rows_per_chunk=8):
+def weighted_median_filter(uv, color, occ, hsz, sigma_i, rows_per_chunk=8, flip=False):
     """denoise_color_weighted_medfilt2 / _wmedfilt_vectorized (weighted_median.py:24-112): window
     (2hsz+1)^2 with numpy 'reflect' padding (mirror, no edge repeat), weight = max(exp(-|dLab|^2 /
-    2 sigma_i^2) * occ_q, 1e-10); per component sort, sequential cumsum, first k with cum >= total/2."""
+    2 sigma_i^2) * occ_q, 1e-10); per component sort, sequential cumsum, first k with cum >= total/2.
+    The reference sorts with np.argsort's default (unstable) kind, so the order of EQUAL flow values -- and with it the
+    rounding of the sequential cumsum -- is an implementation detail of NumPy on the host it ran on.  This restatement
+    sorts stably; flip=True presents the window in reverse order, i.e. the opposite tie order.  Where the two disagree
+    the reference's own answer is summation-order dependent (tests/test_oracle_vs_golden.py::test_weighted_median_tie_fuzz)."""
     H, W = uv.shape[:2]
     if color.ndim == 2:
         color = color[:, :, None]
@@ -728,6 +732,8 @@ def weighted_median_filter(uv, color, occ, hsz, sigma_i, rows_per_chunk=8):
             cw = swv(cp[sl, :, c], (k, k)).reshape(r1 - r0, W, k * k)
             cd += (cw - color[r0:r1, :, c][:, :, None]) ** 2
         wgt = np.maximum(np.exp(-cd * inv) * ow, 1e-10)
+        if flip:
+            uw, vw, wgt = uw[:, :, ::-1], vw[:, :, ::-1], wgt[:, :, ::-1]
         for comp, vals in ((0, uw), (1, vw)):
             order = np.argsort(vals, axis=2, kind="stable")
             vs = np.take_along_axis(vals, order, axis=2)
@@ -736,6 +742,47 @@ def weighted_median_filter(uv, color, occ, hsz, sigma_i, rows_per_chunk=8):
             idx = np.minimum((cw >= half).argmax(axis=2), k * k - 1)
             out[r0:r1, :, comp] = np.take_along_axis(vs, idx[:, :, None], axis=2)[:, :, 0]
     return out
+
+
+def weighted_median_admissible(uv, color, occ, hsz, sigma_i, rows_per_chunk=8):
+    """Test helper for the decision boundary of weighted_median_1d (weighted_median.py:15-21).  With T the window's total
+    weight and S(x) the weight of the samples <= x, the reference returns min{x : S(x) >= T/2} -- evaluated on a
+    SEQUENTIAL fp64 cumsum in a sort order that is arbitrary among equal values.  Where some S(x) lies within the
+    rounding error of that cumsum (delta = n 2^-52 T) of T/2, the reference's own answer depends on summation order.
+    Returns (lo, hi): lo = min{x : S(x) >= T/2 - delta}, hi = min{x : S(x) >= T/2 + delta}, sums in extended precision.
+    lo == hi: the answer is order independent and must be reproduced bit-exactly; otherwise any window value in
+    [lo, hi] is an answer the reference itself may give."""
+    H, W = uv.shape[:2]
+    if color.ndim == 2:
+        color = color[:, :, None]
+    k = 2 * hsz + 1
+    pad2 = ((hsz, hsz), (hsz, hsz))
+    planes = [np.pad(uv[:, :, 0], pad2, mode="reflect"), np.pad(uv[:, :, 1], pad2, mode="reflect")]
+    op = np.pad(occ, pad2, mode="reflect")
+    cp = np.pad(color, pad2 + ((0, 0),), mode="reflect")
+    swv = np.lib.stride_tricks.sliding_window_view
+    inv = 1.0 / (2.0 * sigma_i ** 2)
+    lo, hi = np.empty((H, W, 2)), np.empty((H, W, 2))
+    for r0 in range(0, H, rows_per_chunk):
+        r1 = min(H, r0 + rows_per_chunk)
+        sl = slice(r0, r1 + 2 * hsz)
+        ow = swv(op[sl], (k, k)).reshape(r1 - r0, W, k * k)
+        cd = np.zeros((r1 - r0, W, k * k))
+        for c in range(color.shape[2]):
+            cw = swv(cp[sl, :, c], (k, k)).reshape(r1 - r0, W, k * k)
+            cd += (cw - color[r0:r1, :, c][:, :, None]) ** 2
+        wgt = np.maximum(np.exp(-cd * inv) * ow, 1e-10)
+        for comp in (0, 1):
+            vals = swv(planes[comp][sl], (k, k)).reshape(r1 - r0, W, k * k)
+            order = np.argsort(vals, axis=2, kind="stable")
+            vs = np.take_along_axis(vals, order, axis=2)
+            cwl = np.cumsum(np.take_along_axis(wgt, order, axis=2).astype(np.longdouble), axis=2)
+            T = cwl[:, :, -1:]
+            delta = (k * k) * np.longdouble(2.0) ** -52 * T
+            for dst, thr in ((lo, T / 2 - delta), (hi, T / 2 + delta)):
+                idx = np.minimum((cwl >= thr).argmax(axis=2), k * k - 1)
+                dst[r0:r1, :, comp] = np.take_along_axis(vs, idx[:, :, None], axis=2)[:, :, 0]
+    return lo, hi
 
 
 def nonlocal_filter(uv, color, occ, area_hsz, mfsz, sigma_i):

@@ -124,7 +124,7 @@ def test_batch_equals_single(stages):
     ims1 = np.stack([a, b, a[::-1].copy()])
     ims2 = np.stack([b, a, b[::-1].copy()])
     uv, st = estimate_flow_batch(ims1, ims2, "classic+nl-fast", return_stats=True)
-    assert st["kernel_launches"] > 0 and st["not_converged"] == 0
+    assert st["kernel_launches"] > 0 and st["not_converged"] == 0 and st["kernels"]["solver"]["calls"] == st["solves"]
     for k in range(3):
         single = estimate_flow(ims1[k].astype(float), ims2[k].astype(float), "classic+nl-fast")
         assert_close(uv[k], single, 1e-7, "batch item %d vs single" % k)

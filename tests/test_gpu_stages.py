@@ -152,3 +152,23 @@ def test_weighted_median_other_windows(of, stages):
     for hsz in (1, 2, 4, 5, 9):
         got = of["wm"].denoise_color_weighted_medfilt2(uv, col, occ, hsz, [5, 5], 5.0)
         np.testing.assert_array_equal(got, fo.weighted_median_filter(uv, col, occ, hsz, 5.0), err_msg="hsz=%d" % hsz)
+
+
+def test_weighted_median_tie_fuzz():
+    """The CUDA weighted median on the tie / near-tie fixtures (outputs of the unmodified reference, see
+    test_oracle_vs_golden.py::test_weighted_median_tie_fuzz for the criterion): bit-exact wherever the reference's answer
+    does not depend on its unstable sort's order of equal values, inside the admissible interval elsewhere, bit-exact
+    everywhere when the sums are exact (power-of-two weights)."""
+    import flow_oracle as fo
+    from optical_flow.utils.weighted_median import denoise_color_weighted_medfilt2
+    g = load_golden("wmed_fuzz.npz")
+    for i in range(int(g["ncases"])):
+        uv, col, occ, hsz = g["c%d_uv" % i], g["c%d_col" % i], g["c%d_occ" % i], int(g["c%d_hsz" % i])
+        ref = g["c%d_out" % i]
+        got = denoise_color_weighted_medfilt2(uv, col, occ, hsz, [5, 5], 7, False)
+        lo, hi = fo.weighted_median_admissible(uv, col, occ, hsz, 7.0)
+        assert ((got >= lo) & (got <= hi)).all(), "case %d: %d outside" % (i, int(((got < lo) | (got > hi)).sum()))
+        same = lo == hi
+        np.testing.assert_array_equal(got[same], ref[same], err_msg="case %d" % i)
+        if i == 0:
+            np.testing.assert_array_equal(got, ref, err_msg="exact-arithmetic case")

@@ -196,3 +196,26 @@ def test_sor_oracle_vs_reference():
         p = fo.preset(preset)
         s = fo.assemble(uv, np.zeros_like(uv), g[tag + "_It"], g[tag + "_Ix"], g[tag + "_Iy"], fo._spec(p), 0.0)
         assert maxabs(fo.sor_solve(s), g[tag + "_x"]) <= 1e-12
+
+
+def test_weighted_median_tie_fuzz():
+    """Decision boundary of weighted_median_1d (weighted_median.py:15-21) on fixtures built to sit on it
+    (tests/golden/gen_golden_wmfuzz.py, outputs of the unmodified reference).  The reference's np.argsort is unstable, so
+    among EQUAL flow values its summation order -- and the last bit of its cumsum -- is an implementation detail; the
+    oracle must agree bit-exactly wherever the answer does not depend on that (weighted_median_admissible: lo == hi), stay
+    inside [lo, hi] elsewhere, and agree everywhere when every sum is exact (power-of-two weights, case 0)."""
+    g = load_golden("wmed_fuzz.npz")
+    boundary = 0
+    for i in range(int(g["ncases"])):
+        args = (g["c%d_uv" % i], g["c%d_col" % i], g["c%d_occ" % i], int(g["c%d_hsz" % i]), 7.0)
+        ref = g["c%d_out" % i]
+        lo, hi = fo.weighted_median_admissible(*args)
+        got = fo.weighted_median_filter(*args)
+        assert ((ref >= lo) & (ref <= hi)).all(), "case %d: the reference itself leaves the admissible interval" % i
+        assert ((got >= lo) & (got <= hi)).all(), "case %d" % i
+        same = lo == hi
+        np.testing.assert_array_equal(got[same], ref[same], err_msg="case %d" % i)
+        if i == 0:
+            np.testing.assert_array_equal(got, ref, err_msg="exact-arithmetic case")
+        boundary += int((~same).sum())
+    assert boundary > 50, "the fixtures no longer reach the decision boundary"
