@@ -121,6 +121,20 @@ int  b200flow_ctx_set_timing(b200flow_ctx *ctx, int enabled);   /* per-stage CUD
  * another.  solver_ctas_per_sm = CTAs per SM each group's persistent solver takes (0: an equal share).  groups = 1
  * (default) is the plain single-stream pipeline.  Results are identical either way (pairs are independent). */
 int  b200flow_ctx_set_split(b200flow_ctx *ctx, int groups, int solver_ctas_per_sm);
+/* Row-band split of ONE pair over the GPUs of a box (no counterpart in the reference; the loop it accelerates is the solve
+ * inside ba.py:140-206 / classic_nl.py:200-277).  One process per GPU; every rank calls the ordinary b200flow_estimate*
+ * entry points with the SAME arguments, and every linear solve of a level with at least 2^18 pixels is iterated band-wise:
+ * rank g owns a band of rows, reads one halo row of two Krylov vectors from each neighbour over NVLink P2P per iteration,
+ * and the dot products travel through peer-mapped flags (no NCCL, no host).  All other stages are replicated.
+ *   band_init     replaces the context arena by ONE device block of arena_bytes (it must hold a whole call);
+ *                 same_device != 0: two ranks emulated on one GPU by two contexts of one process (tests)
+ *   band_export   the block's 64-byte CUDA IPC handle (to be all-gathered by the caller) and/or its address
+ *   band_connect  maps peer `peer`'s block: from its IPC handle, or (same process) from its address
+ *   band_close    leaves row-band mode; reports a timed-out cross-GPU barrier as B200FLOW_ECUDA */
+int  b200flow_band_init(b200flow_ctx *ctx, int rank, int world, unsigned long long arena_bytes, int same_device);
+int  b200flow_band_export(b200flow_ctx *ctx, void *handle64, void **base);
+int  b200flow_band_connect(b200flow_ctx *ctx, int peer, const void *handle64, void *base);
+int  b200flow_band_close(b200flow_ctx *ctx);
 int  b200flow_ctx_sync(b200flow_ctx *ctx);
 void *b200flow_ctx_stream(b200flow_ctx *ctx);               /* the cudaStream_t, for torch / event interop */
 int  b200flow_ctx_num_sms(const b200flow_ctx *ctx);

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 
 namespace bf {
+int k_band_error(b200flow_ctx *ctx, unsigned long long *err_host);
 PenaltySet make_penalty_set(const b200flow_params *p, double alpha);
 int alloc_linsys(b200flow_ctx *ctx, int B, int H, int W, LinSys *s);
 }  // namespace bf
@@ -11,6 +12,7 @@ int alloc_linsys(b200flow_ctx *ctx, int B, int H, int W, LinSys *s);
 using namespace bf;
 
 static std::string g_create_err;
+extern "C" { static void band_release(b200flow_ctx *ctx); }
 
 #define API_BEGIN(ctx)                                                      \
   if (!(ctx)) return B200FLOW_EINVAL;                                       \
@@ -76,6 +78,7 @@ void b200flow_ctx_destroy(b200flow_ctx *ctx) {
     if (c->ev_s1) cudaEventDestroy(c->ev_s1);
     delete c;
   }
+  band_release(ctx);
   for (auto e : ctx->ev_join) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaStreamSynchronize(ctx->stream);
@@ -99,6 +102,92 @@ int b200flow_ctx_set_split(b200flow_ctx *ctx, int groups, int solver_ctas_per_sm
     return set_err(ctx, B200FLOW_EINVAL, "concurrent sub-batches: groups %d (1..8), solver CTAs per SM %d (>= 0)", groups, solver_ctas_per_sm);
   ctx->nsplit = groups;
   ctx->solver_ctas_per_sm = solver_ctas_per_sm;
+  return 0;
+}
+
+// ---- row-band split of one pair over several GPUs ---------------------------------------------------------------------
+static void band_release(b200flow_ctx *ctx) {
+  for (int r = 0; r < B200FLOW_MAX_BAND_RANKS; ++r) {
+    if (ctx->band.opened[r] && ctx->band.base[r]) cudaIpcCloseMemHandle(ctx->band.base[r]);
+    ctx->band.opened[r] = false;
+    ctx->band.base[r] = nullptr;
+  }
+  ctx->band.world = 1;
+  ctx->band.rank = 0;
+  ctx->band.ticket = nullptr;
+}
+
+int b200flow_band_init(b200flow_ctx *ctx, int rank, int world, unsigned long long arena_bytes, int same_device) {
+  if (!ctx) return B200FLOW_EINVAL;
+  if (world < 1 || world > B200FLOW_MAX_BAND_RANKS || rank < 0 || rank >= world)
+    return set_err(ctx, B200FLOW_EINVAL, "row-band mode: rank %d of %d (at most %d ranks)", rank, world, B200FLOW_MAX_BAND_RANKS);
+  BF_CUDA(ctx, cudaSetDevice(ctx->device));
+  BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  band_release(ctx);
+  for (auto &c : ctx->chunks) cudaFree(c.base);
+  ctx->chunks.clear();
+  if (world == 1) return 0;
+  if (arena_bytes < ((size_t)64 << 20)) arena_bytes = (size_t)64 << 20;
+  char *p = nullptr;
+  BF_CUDA(ctx, cudaMalloc(&p, (size_t)arena_bytes));      // ONE block: it is mapped into the peers and must never move
+  BF_CUDA(ctx, cudaMemset(p, 0, B200FLOW_BAND_RESERVED));
+  ctx->chunks.push_back({p, (size_t)arena_bytes, B200FLOW_BAND_RESERVED});
+  ctx->band.rank = rank;
+  ctx->band.world = world;
+  ctx->band.base[rank] = p;
+  ctx->band.ticket = reinterpret_cast<unsigned *>(p + B200FLOW_BAND_RESERVED / 2);
+  if (const char *mp = getenv("B200FLOW_BAND_MIN_PIXELS")) ctx->band.min_pixels = atoll(mp);
+  if (same_device) {        // several ranks emulated on one GPU (tests): every rank's persistent solver must stay resident
+    ctx->plain_solver_launch = true;
+    ctx->solver_ctas_per_sm = 1;
+    if (world > 2) return set_err(ctx, B200FLOW_EINVAL, "same-device emulation holds two ranks");
+  }
+  return 0;
+}
+
+int b200flow_band_export(b200flow_ctx *ctx, void *handle64, void **base) {
+  if (!ctx || ctx->band.world < 2) return B200FLOW_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (base) *base = ctx->band.base[ctx->band.rank];
+  if (handle64) {
+    cudaIpcMemHandle_t h;
+    BF_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->band.base[ctx->band.rank]));
+    memcpy(handle64, &h, 64);
+  }
+  return 0;
+}
+
+int b200flow_band_connect(b200flow_ctx *ctx, int peer, const void *handle64, void *base) {
+  if (!ctx || ctx->band.world < 2 || peer < 0 || peer >= ctx->band.world || peer == ctx->band.rank)
+    return ctx ? set_err(ctx, B200FLOW_EINVAL, "row-band connect: bad peer %d", peer) : B200FLOW_EINVAL;
+  BF_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (base) {               // same process: the peer's block is addressable as it is (same device, or peer access enabled)
+    ctx->band.base[peer] = static_cast<char *>(base);
+    ctx->band.opened[peer] = false;
+    return 0;
+  }
+  if (!handle64) return set_err(ctx, B200FLOW_EINVAL, "row-band connect: neither a handle nor a base pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  BF_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->band.base[peer] = static_cast<char *>(p);
+  ctx->band.opened[peer] = true;
+  return 0;
+}
+
+int b200flow_band_close(b200flow_ctx *ctx) {
+  if (!ctx) return B200FLOW_EINVAL;
+  BF_CUDA(ctx, cudaSetDevice(ctx->device));
+  BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned long long err = 0;
+  if (ctx->band.world > 1) BF_TRY(k_band_error(ctx, &err));
+  band_release(ctx);
+  for (auto &c : ctx->chunks) cudaFree(c.base);
+  ctx->chunks.clear();
+  ctx->plain_solver_launch = false;
+  ctx->solver_ctas_per_sm = 0;
+  if (err) return set_err(ctx, B200FLOW_ECUDA, "row-band mode: a cross-GPU barrier timed out (barrier %llu): a peer rank stopped", err);
   return 0;
 }
 

@@ -10,6 +10,18 @@
 #include <vector>
 #include "../../include/b200flow.h"
 
+#define B200FLOW_MAX_BAND_RANKS 8
+#define B200FLOW_BAND_RESERVED 4096      // head of the arena block: cross-GPU barrier state (solve_ic.cu BandSync) + ticket
+
+// row-band split of one pair over several GPUs (b200flow_band_* in include/b200flow.h)
+struct b200flow_band {
+  int rank = 0, world = 1;
+  char *base[B200FLOW_MAX_BAND_RANKS] = {nullptr};   // every rank's arena block as mapped in this process (base[rank] = own)
+  bool opened[B200FLOW_MAX_BAND_RANKS] = {false};    // mapped through cudaIpcOpenMemHandle (to be closed)
+  unsigned *ticket = nullptr;                        // device counter of band_push_kernel (inside the reserved head)
+  long long min_pixels = 1 << 18;                    // levels below this many pixels are solved by every rank on its own
+};
+
 struct b200flow_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -38,6 +50,7 @@ struct b200flow_ctx {
   cudaStream_t solver_stream = nullptr;   // children only: high-priority stream the persistent solver is launched on, so
                                           // that its CTAs are dispatched ahead of a sibling's pending weighted-median CTAs
   cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
+  b200flow_band band;
   b200flow_ctx *parent = nullptr;
   std::vector<b200flow_ctx *> subs; // child contexts (own stream + arena), created on demand
   cudaEvent_t ev_fork = nullptr;
@@ -87,7 +100,7 @@ inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 // ---- arena -------------------------------------------------------------------------------------
 inline void arena_reset(b200flow_ctx *ctx) {
   // consolidate into one chunk sized for the high-water mark so steady state never cudaMallocs
-  if (ctx->chunks.size() > 1) {
+  if (ctx->chunks.size() > 1 && ctx->band.world <= 1) {
     size_t total = 0;
     for (auto &c : ctx->chunks) { total += c.size; cudaFree(c.base); }
     ctx->chunks.clear();
@@ -95,6 +108,7 @@ inline void arena_reset(b200flow_ctx *ctx) {
     if (cudaMalloc(&p, total) == cudaSuccess) ctx->chunks.push_back({p, total, 0});
   }
   for (auto &c : ctx->chunks) c.off = 0;
+  if (ctx->band.world > 1 && !ctx->chunks.empty()) ctx->chunks[0].off = B200FLOW_BAND_RESERVED;   // barrier state lives here
   ctx->in_use = 0;
 }
 
@@ -109,6 +123,7 @@ inline void *arena_alloc_raw(b200flow_ctx *ctx, size_t bytes) {
       return p;
     }
   }
+  if (ctx->band.world > 1) return nullptr;   // row-band mode: the block is mapped into the peers and must not move or grow
   size_t sz = bytes;
   size_t grow = ctx->chunks.empty() ? (size_t(64) << 20) : ctx->chunks.back().size * 2;
   if (sz < grow) sz = grow;

@@ -405,7 +405,8 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
   __shared__ double s_rz[MAXB], s_bb[MAXB], s_alpha[MAXB], s_beta[MAXB], s_maxr2[MAXB], s_rzprev[MAXB];
   __shared__ double s_ta[MAXB], s_tb[MAXB];
   __shared__ int s_state[MAXB];          // 0 active, 1 finished, 2 converged: final flush pending, 3 reliable update in progress
-  __shared__ int s_bad[MAXB], s_flush[MAXB];
+  __shared__ int s_bad[MAXB], s_flush[MAXB], s_restarts[MAXB], s_stalls[MAXB];
+  __shared__ double s_lasttrue[MAXB];
   __shared__ int s_act[MAXB], s_pos[MAXB];   // compact list of unfinished systems and its inverse
   __shared__ int s_nact, s_tpc;
 
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
   }
 
   // ---------------- init ----------------
-  for (int b = tid; b < MAXB; b += PCG_THREADS) { s_state[b] = b < B ? 0 : 1; s_bad[b] = 0; s_flush[b] = 0; }
+  for (int b = tid; b < MAXB; b += PCG_THREADS) { s_state[b] = b < B ? 0 : 1; s_bad[b] = 0; s_flush[b] = 0; s_restarts[b] = 0; s_stalls[b] = 0; s_lasttrue[b] = 1e300; }
   REMAP()
   {
     OWN_RANGE()
@@ -660,7 +661,15 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
         const int b = tid;
         double rz = s_ta[b], rr = s_tb[b];
         int conv = rr <= P.tol2 * s_bb[b];
-        if (conv || s_bad[b] || !(rz > 0.0) || !(rr == rr) || k + 1 == P.maxit) {
+        // An fp32 breakdown (p.Ap <= 0, r.z <= 0: the iterated quantities have lost their meaning close to the fp32
+        // floor) is not the end: the fp64 residual and z = M^-1 r just computed are sound, so CG RESTARTS from them
+        // (beta = 0).  Given up after 8 restarts, or when three replacements in a row failed to halve the true residual
+        // (the fp64 floor of an ill-conditioned system: attainable accuracy reached).
+        const int fatal = !(rz > 0.0) || !(rr == rr) || k + 1 == P.maxit;
+        if (s_bad[b]) s_restarts[b] += 1;
+        s_stalls[b] = rr > 0.25 * s_lasttrue[b] ? s_stalls[b] + 1 : 0;
+        s_lasttrue[b] = rr;
+        if (conv || fatal || s_restarts[b] > 8 || s_stalls[b] >= 3) {
           s_state[b] = 2;
           fin = 1;
           if (cta == C_LO(b)) {
@@ -672,7 +681,7 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
           s_state[b] = 0;
           s_flush[b] = 1;                                  // x += y + alpha_k p_k rides on the next phase A
           s_maxr2[b] = rr;
-          s_beta[b] = rz / s_rzprev[b];
+          s_beta[b] = s_bad[b] ? 0.0 : rz / s_rzprev[b];   // restart after a breakdown: p = z
           s_rz[b] = rz;
         }
       }
@@ -892,7 +901,14 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     P.m.Ap = reinterpret_cast<float2 *>(w.p2); P.m.y = P.m.Ap + n;
     P.m.D = reinterpret_cast<float2 *>(w.z);   P.m.WH = P.m.D + n;
     P.m.WV = reinterpret_cast<float2 *>(w.Ap); P.m.a12 = reinterpret_cast<float *>(P.m.WV + n);
-    if (mode == PCG_MODE_MIXED_IC) {
+    if (mode == PCG_MODE_MIXED_IC && ctx->band.world > 1 && sys.B == 1 &&
+        (long long)sys.H * sys.W >= ctx->band.min_pixels && (sys.H + 7) / 8 >= ctx->band.world) {
+      // row-band mode: this rank iterates on its rows only, then the solution bands are exchanged (solve_ic.cu)
+      BF_TRY(k_pcg_ic_band_launch(ctx, P, w.grid_ic));
+      ctx->launches++;
+      BF_TRY(k_band_exchange_x(ctx, x, sys.H, sys.W));
+      ctx->launches--;                 // (the common exit below counts the solver launch)
+    } else if (mode == PCG_MODE_MIXED_IC) {
       BF_TRY(k_pcg_ic_launch(ctx, P, w.grid_ic));
     } else {
       void *args[] = {&P};

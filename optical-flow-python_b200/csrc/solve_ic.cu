@@ -270,9 +270,134 @@ __device__ __forceinline__ void ic_factor(const IcSmem sm, int w, int lane) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Row-band split of ONE system over several GPUs (reference loop: ba.py:140-206, one solve per warp
+// iteration).  Rank g owns the pixel rows [y0, y1) (multiples of 8, so the 8 x 8 IC sub-tiles never straddle a band and the
+// preconditioner -- hence every iterate -- is the one the single-GPU solve has).  Every rank holds the full coefficient
+// arrays (the assembly is replicated); the Krylov vectors live band-local at the SAME offsets of every rank's arena, which
+// is one cudaMalloc block mapped into the peers by CUDA IPC: a neighbour's row is read by adding the byte distance between
+// the two blocks to the local pointer (direct NVLink P2P loads, no staging, no NCCL).
+//   per iteration:  phase A reads ONE row of z and of p_old from each neighbour band (2 x W x 8 B per side);
+//                   each of the two barriers carries the rank-local dot products to every peer (2 doubles, pushed by
+//                   CTA 0 over NVLink) and waits for the peers' sequence flags -- no host, no collective library.
+// All ranks sum the per-rank scalars in rank order, so every rank (and every CTA) takes bit-identical control decisions.
+// ------------------------------------------------------------------------------------------------------------------
+struct BandSync {                        // at offset 0 of every rank's arena block
+  unsigned long long seq;                // barriers this rank has completed (written by its CTA 0 only; persists across kernels)
+  unsigned long long release;            // local release: this rank's CTAs may leave barrier `release`
+  unsigned long long flag[B200FLOW_MAX_BAND_RANKS];     // flag[r]: last barrier rank r has arrived at (written by rank r, remotely)
+  double xs[2][B200FLOW_MAX_BAND_RANKS][2];             // xs[parity][r]: rank r's local sums of that barrier (written by rank r)
+  double gs[2][2];                       // the global sums of that barrier (written by the local CTA 0)
+  unsigned long long error;              // != 0: a spin loop timed out (a peer died); the result is invalid
+};
+
+struct BandParams {
+  int rank, world, y0, y1;               // this rank's rows
+  long long up_delta, dn_delta;          // byte distance from this rank's block to the block of the rank above / below (0: none)
+  BandSync *self;
+  BandSync *peer[B200FLOW_MAX_BAND_RANKS];   // every rank's BandSync as mapped here (peer[rank] == self)
+};
+
+__device__ __forceinline__ void st_sys_f64(double *p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_sys_f64(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// neighbour-band rows: coherent at system scope, never from this SM's L1
+__device__ __forceinline__ float2 ld_sys_f2(const float2 *p) {
+  float2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 ld_sys_d2(const double2 *p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ const T *band_shift(const T *p, long long delta) {
+  return reinterpret_cast<const T *>(reinterpret_cast<const char *>(p) + delta);
+}
+constexpr long long BAND_SPIN_LIMIT = 1LL << 25;       // ~ 10-20 s of polling: a dead peer must not hang the GPU
+
+// Barrier + reduction of the band solver.  All CTAs arrive on the local monotonic counter; CTA 0 waits for them, reduces the
+// rank-local partials pa / pb (slots c_lo .. c_hi) in a fixed order, pushes the two sums and then its sequence flag to every
+// rank, waits for every rank's flag, sums the per-rank values in rank order and releases the local CTAs.  Returns the
+// global sums in every thread.
+__device__ __forceinline__ void band_barrier_reduce(const BandParams &bp, unsigned *arrive, unsigned &target,
+                                                    unsigned long long &seq, const double *pa, const double *pb, int c_lo,
+                                                    int c_hi, double &ga, double &gb) {
+  __syncthreads();
+  seq += 1;
+  const int slot = (int)(seq & 1ull);
+  BandSync *self = bp.self;
+  // once a barrier has timed out every later one gives up at once and hands NaN sums to the solver, which then stops
+  const long long limit = *(volatile unsigned long long *)&self->error != 0ull ? 0 : BAND_SPIN_LIMIT;
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(arrive, 1u);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    long long spins = 0;
+    if (lane == 0) {
+      while (*(volatile unsigned *)arrive < target && ++spins < limit) {}
+      __threadfence();
+    }
+    __syncwarp();
+    double va = 0.0, vb = 0.0;
+    for (int c = c_lo + lane; c <= c_hi; c += 32) {
+      va += ((const volatile double *)pa)[c];
+      if (pb) vb += ((const volatile double *)pb)[c];
+    }
+    va = warp_sum(va);
+    vb = warp_sum(vb);
+    if (lane == 0) {
+      for (int r = 0; r < bp.world; ++r) {
+        st_sys_f64(&bp.peer[r]->xs[slot][bp.rank][0], va);
+        st_sys_f64(&bp.peer[r]->xs[slot][bp.rank][1], vb);
+      }
+      __threadfence_system();                       // the band's vectors and the sums, before the flag
+      for (int r = 0; r < bp.world; ++r) st_release_sys_u64(&bp.peer[r]->flag[bp.rank], seq);
+      for (int r = 0; r < bp.world; ++r)
+        while (ld_acquire_sys_u64(&self->flag[r]) < seq && ++spins < limit) {}
+      double sa = 0.0, sb = 0.0;
+      for (int r = 0; r < bp.world; ++r) { sa += ld_sys_f64(&self->xs[slot][r][0]); sb += ld_sys_f64(&self->xs[slot][r][1]); }
+      if (spins >= limit) {                         // timed out (now or earlier): poison the sums, the solve ends as failed
+        if (limit > 0) self->error = seq;
+        sa = sb = __longlong_as_double(0x7ff8000000000000LL);
+      }
+      self->gs[slot][0] = sa;
+      self->gs[slot][1] = sb;
+      self->seq = seq;
+      __threadfence();
+      *(volatile unsigned long long *)&self->release = seq;
+    }
+  }
+  if (threadIdx.x == 0) {
+    long long spins = 0;
+    while (*(volatile unsigned long long *)&self->release < seq && ++spins < 4 * BAND_SPIN_LIMIT) {}
+    __threadfence();
+  }
+  __syncthreads();
+  ga = ((volatile double *)self->gs[slot])[0];
+  gb = ((volatile double *)self->gs[slot])[1];
+}
+
 // true residual at pixel i of the solution x + y + alpha p, fp64, evaluated on the fly at the five stencil points
-__device__ __forceinline__ double2 ic_true_residual(const MixParams &P, long long i, int px, int py, const float2 *pnew,
-                                                    double alpha) {
+template <bool BAND>
+__device__ __forceinline__ double2 ic_true_residual(const MixParams &P, const BandParams &bp, long long i, int px, int py,
+                                                    const float2 *pnew, double alpha) {
   const LinSys &S = P.sys;
   const int W = S.W, H = S.H;
   const double2 *x = P.x;
@@ -285,9 +410,20 @@ __device__ __forceinline__ double2 ic_true_residual(const MixParams &P, long lon
     out = make_double2(xx.x + ((double)yy.x + alpha * (double)pp.x),            \
                        xx.y + ((double)yy.y + alpha * (double)pp.y));           \
   }
+  // a row of the neighbour band: the same offsets in the neighbour's arena block, read over NVLink
+#define XTRUE_PEER(j, delta, out)                                               \
+  {                                                                             \
+    double2 xx = ld_sys_d2(band_shift(x + (j), delta));                         \
+    float2 yy = ld_sys_f2(band_shift(y + (j), delta)), pp = ld_sys_f2(band_shift(pnew + (j), delta)); \
+    out = make_double2(xx.x + ((double)yy.x + alpha * (double)pp.x),            \
+                       xx.y + ((double)yy.y + alpha * (double)pp.y));           \
+  }
   double2 c, nl, nr, nu, nd;
-  XTRUE(i, c) XTRUE(jl, nl) XTRUE(jr, nr) XTRUE(ju, nu) XTRUE(jd, nd)
+  XTRUE(i, c) XTRUE(jl, nl) XTRUE(jr, nr)
+  if (BAND && py == bp.y0 && bp.up_delta != 0) XTRUE_PEER(ju, bp.up_delta, nu) else XTRUE(ju, nu)
+  if (BAND && py + 1 == bp.y1 && bp.dn_delta != 0) XTRUE_PEER(jd, bp.dn_delta, nd) else XTRUE(jd, nd)
 #undef XTRUE
+#undef XTRUE_PEER
   const double2 sd = __ldg(&S.D[i]), swr = __ldg(&S.WH[i]), swd = __ldg(&S.WV[i]);
   const double2 swl = __ldg(&S.WH[jl]), swu = __ldg(&S.WV[ju]);   // multiplied by a zero difference when jl == i / ju == i
   const double sa12 = __ldg(&S.a12[i]);
@@ -328,11 +464,15 @@ __device__ __forceinline__ void ic_grid_barrier(unsigned *counter, unsigned &tar
 #define IC_GRID_SYNC() grid.sync()
 #endif
 
-__global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(MixParams P) {
+
+template <bool BAND>
+__device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams &bp) {
 #ifdef IC_CG_BARRIER
   cg::grid_group grid = cg::this_grid();
 #endif
   const LinSys &S = P.sys;
+  const int Y0 = BAND ? bp.y0 : 0;                 // first pixel row of this rank's band
+  const int Y1 = BAND ? bp.y1 : S.H;               // one past its last row
   const int G = gridDim.x, cta = blockIdx.x;
   const int H = S.H, W = S.W, B = S.B;
   const long long HW = (long long)H * W;
@@ -356,7 +496,8 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   __shared__ double s_rz[MAXB], s_bb[MAXB], s_alpha[MAXB], s_beta[MAXB], s_maxr2[MAXB], s_rzprev[MAXB];
   __shared__ double s_ta[MAXB], s_tb[MAXB];
   __shared__ int s_state[MAXB];          // 0 active, 1 finished, 2 converged: final flush pending, 3 reliable update in progress
-  __shared__ int s_bad[MAXB], s_flush[MAXB];
+  __shared__ int s_bad[MAXB], s_flush[MAXB], s_restarts[MAXB], s_stalls[MAXB];
+  __shared__ double s_lasttrue[MAXB];
   __shared__ int s_act[MAXB], s_pos[MAXB];   // compact list of unfinished systems and its inverse
   __shared__ int s_nact, s_tpc;
 
@@ -379,6 +520,8 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   unsigned *bar_counter = reinterpret_cast<unsigned *>(P.w.flags);   // flags[0]: zeroed before every launch
   unsigned bar_target = 0u;
 #endif
+  unsigned long long band_seq = 0ull;
+  if (BAND) band_seq = *(volatile unsigned long long *)&bp.self->seq;   // this rank's barrier count so far (own writes only)
   int *iters_g = P.w.flags + 1 + B;
   double *relres_g = P.w.scal;
 
@@ -417,10 +560,26 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   {                                                                                              \
     const int tl = (int)((v) - tbase);                                                           \
     px = (tl % P.tiles_x) * 32 + tx;                                                             \
-    py = (tl / P.tiles_x) * 8 + ty;                                                              \
-    ok = (v) < tb && px < W && py < H;                                                           \
+    py = Y0 + (tl / P.tiles_x) * 8 + ty;                                                         \
+    ok = (v) < tb && px < W && py < Y1;                                                          \
     i = ok ? base + (long long)py * W + px : base;                                               \
   }
+  // barrier + reduction of one phase: single GPU = the grid barrier, then every CTA re-reduces the partials; band mode =
+  // band_barrier_reduce (one system, CTA 0 reduces and exchanges with the peers)
+#ifdef IC_CG_BARRIER
+#define SYNC_REDUCE(pa, pb, want) { IC_GRID_SYNC(); REDUCE_ALL(pa, pb, want) }
+#else
+#define SYNC_REDUCE(pa, pb, want)                                                               \
+  if (BAND) {                                                                                   \
+    double ga_, gb_;                                                                            \
+    band_barrier_reduce(bp, bar_counter, bar_target, band_seq, (pa), (pb), C_LO(0), C_HI(0), ga_, gb_);   \
+    if (tid == 0) { s_ta[0] = ga_; s_tb[0] = gb_; }                                             \
+    __syncthreads();                                                                            \
+  } else {                                                                                      \
+    IC_GRID_SYNC();                                                                             \
+    REDUCE_ALL(pa, pb, want)                                                                    \
+  }
+#endif
 #define REDUCE_ALL(pa, pb, want)                                                        \
   {                                                                                     \
     const int b = tid / GW, gl = tid % GW;                                              \
@@ -449,13 +608,13 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   {                                                                                                            \
     const int tl = (int)((t) - tbase);                                                                         \
     const int px = (tl % P.tiles_x) * 32 + tx;                                                                 \
-    const int py0 = (tl / P.tiles_x) * 8;                                                                      \
+    const int py0 = Y0 + (tl / P.tiles_x) * 8;                                                                 \
     const long long i0 = base + (long long)py0 * W + px;                                                       \
     const int sl0 = ic_slot(ty * 8, tx);                                                                       \
     float2 rc[8], ac[8];                                                                                       \
     _Pragma("unroll")                                                                                          \
     for (int u = 0; u < 8; ++u) {                                                                              \
-      const bool ok = px < W && py0 + u < H;                                                                   \
+      const bool ok = px < W && py0 + u < Y1;                                                                  \
       const long long ii = ok ? i0 + (long long)u * W : base;                                                  \
       cp_async16(sm.c0 + (sl0 + u * IC_PITCH) * 16, C0 + ii, ok ? 16 : 0);                                     \
       cp_async4(sm.cw + (sl0 + u * IC_PITCH) * 4, CW + ii, ok ? 4 : 0);                                        \
@@ -465,7 +624,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
     float prr = 0.f, prz = 0.f;                                                                                \
     _Pragma("unroll")                                                                                          \
     for (int u = 0; u < 8; ++u) {                                                                              \
-      const bool ok = px < W && py0 + u < H;                                                                   \
+      const bool ok = px < W && py0 + u < Y1;                                                                  \
       float2 v = make_float2(0.f, 0.f);                                                                        \
       if (ok) {                                                                                                \
         v = (use_ap) ? make_float2(fmaf(-(alpha_f), ac[u].x, rc[u].x), fmaf(-(alpha_f), ac[u].y, rc[u].y)) : rc[u]; \
@@ -482,7 +641,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
     __syncwarp();                                                                                              \
     _Pragma("unroll")                                                                                          \
     for (int u = 0; u < 8; ++u) {                                                                              \
-      if (px < W && py0 + u < H) {                                                                             \
+      if (px < W && py0 + u < Y1) {                                                                            \
         const float2 zz = lds64(sm.r + (sl0 + u * IC_PITCH) * 8);                                              \
         z[i0 + (long long)u * W] = zz;                                                                         \
         prz = fmaf(rc[u].x, zz.x, fmaf(rc[u].y, zz.y, prz));                                                   \
@@ -492,7 +651,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
   }
 
   // ---------------- init ----------------
-  for (int b = tid; b < MAXB; b += IC_THREADS) { s_state[b] = b < B ? 0 : 1; s_bad[b] = 0; s_flush[b] = 0; }
+  for (int b = tid; b < MAXB; b += IC_THREADS) { s_state[b] = b < B ? 0 : 1; s_bad[b] = 0; s_flush[b] = 0; s_restarts[b] = 0; s_stalls[b] = 0; s_lasttrue[b] = 1e300; }
   REMAP()
   {
     OWN_RANGE()
@@ -502,7 +661,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
       for (long long t = ta + ty; t < tb; t += IC_NSTRIP) {     // strips of this CTA, dealt round-robin to its warps
         const int tl = (int)(t - tbase);
         const int px = (tl % P.tiles_x) * 32 + tx;
-        const int py0 = (tl / P.tiles_x) * 8;
+        const int py0 = Y0 + (tl / P.tiles_x) * 8;
 #pragma unroll 2
         for (int u = 0; u < 8; ++u) {
           const int py = py0 + u;
@@ -510,7 +669,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
           float2 v = make_float2(0.f, 0.f);
           float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
           unsigned cw = 0u;
-          if (px < W && py < H) {
+          if (px < W && py < Y1) {
             const long long i = base + (long long)py * W + px;
             const Stencil s = load_stencil(S, i, px, py);
             const double duu = s.d.x + s.wr.x + s.wl.x + s.wd.x + s.wu.x;
@@ -541,7 +700,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
 #pragma unroll 2
         for (int u = 0; u < 8; ++u) {
           const int py = py0 + u;
-          if (px < W && py < H) {
+          if (px < W && py < Y1) {
             const long long i = base + (long long)py * W + px;
             const int sl = ic_slot(ty * 8 + u, tx);
             const float2 zz = lds64(sm.r + sl * 8), rv = r[i];
@@ -556,8 +715,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
       if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_bb; }
     }
   }
-  IC_GRID_SYNC();
-  REDUCE_ALL(part_b, part_c, 0)
+  SYNC_REDUCE(part_b, part_c, 0)
   if (tid < B) {
     const int b = tid;
     double rz = s_ta[b], bb = s_tb[b];
@@ -602,9 +760,18 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
           const long long ju = ii >= W ? ii - W : 0, jd = ii + W < n_all ? ii + W : n_all - 1;
           zc[u] = z[ii]; po[u] = pold[ii];
           zl[u] = z[jl]; pl[u] = pold[jl]; zr[u] = z[jr]; pr[u] = pold[jr];
-          zu[u] = z[ju]; pu[u] = pold[ju]; zd[u] = z[jd]; pd[u] = pold[jd];
+          if (BAND && py[u] == Y0 && bp.up_delta != 0) {          // the row above lives in the neighbour's block
+            zu[u] = ld_sys_f2(band_shift(z + ju, bp.up_delta)); pu[u] = ld_sys_f2(band_shift(pold + ju, bp.up_delta));
+          } else { zu[u] = z[ju]; pu[u] = pold[ju]; }
+          if (BAND && py[u] + 1 == Y1 && bp.dn_delta != 0) {
+            zd[u] = ld_sys_f2(band_shift(z + jd, bp.dn_delta)); pd[u] = ld_sys_f2(band_shift(pold + jd, bp.dn_delta));
+          } else { zd[u] = z[jd]; pd[u] = pold[jd]; }
           sd[u] = __ldg(&Df[ii]); swr[u] = __ldg(&WHf[ii]); swd[u] = __ldg(&WVf[ii]);
-          swl[u] = __ldg(&WHf[jl]); swu[u] = __ldg(&WVf[ju]);
+          swl[u] = __ldg(&WHf[jl]);
+          if (BAND && py[u] == Y0) {                              // the fp32 copy only covers the band: take the fp64 edge
+            const double2 e = __ldg(&S.WV[ju]);
+            swu[u] = make_float2((float)e.x, (float)e.y);
+          } else swu[u] = __ldg(&WVf[ju]);
           sa12[u] = __ldg(&a12f[ii]);
           yc[u] = y[ii];
         }
@@ -643,9 +810,8 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
       if (tid == 0) part_a[(long long)b * G + cta] = acc;
     }
     IC_TICK(tmA)
-    IC_GRID_SYNC();
+    SYNC_REDUCE(part_a, (const double *)nullptr, 0)
     IC_TICK(tmS1)
-    REDUCE_ALL(part_a, (const double *)nullptr, 0)
     if (tid < B && s_state[tid] == 0) {
       double pap = s_ta[tid];
       s_alpha[tid] = pap > 0.0 ? s_rz[tid] / pap : 0.0;      // 0 => breakdown, resolved by the reliable update below
@@ -662,9 +828,8 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
       if (tid == 0) { part_b[(long long)b * G + cta] = acc_rz; part_c[(long long)b * G + cta] = acc_rr; }
     }
     IC_TICK(tmB)
-    IC_GRID_SYNC();
+    SYNC_REDUCE(part_b, part_c, 0)
     IC_TICK(tmS2)
-    REDUCE_ALL(part_b, part_c, 0)
     int rel = 0;
     if (tid < B && s_state[tid] == 0) {
       const int b = tid;
@@ -689,7 +854,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
           int px, py; long long i; bool ok;
           PIXEL_OF(v, px, py, i, ok)
           if (!ok) continue;
-          const double2 rt = ic_true_residual(P, i, px, py, pnew, alpha);
+          const double2 rt = ic_true_residual<BAND>(P, bp, i, px, py, pnew, alpha);
           r[i] = make_float2((float)rt.x, (float)rt.y);
           acc_rr += rt.x * rt.x + rt.y * rt.y;
         }
@@ -698,14 +863,21 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
         ic_block_sum2(acc_rz, acc_rr, sm_red);
         if (tid == 0) { part_d[(long long)b * G + cta] = acc_rz; part_e[(long long)b * G + cta] = acc_rr; }
       }
-      IC_GRID_SYNC();
-      REDUCE_ALL(part_d, part_e, 3)
+      SYNC_REDUCE(part_d, part_e, 3)
       int fin = 0;
       if (tid < B && s_state[tid] == 3) {
         const int b = tid;
         double rz = s_ta[b], rr = s_tb[b];
         int conv = rr <= P.tol2 * s_bb[b];
-        if (conv || s_bad[b] || !(rz > 0.0) || !(rr == rr) || k + 1 == P.maxit) {
+        // An fp32 breakdown (p.Ap <= 0, r.z <= 0: the iterated quantities have lost their meaning close to the fp32
+        // floor) is not the end: the fp64 residual and z = M^-1 r just computed are sound, so CG RESTARTS from them
+        // (beta = 0).  Given up after 8 restarts, or when three replacements in a row failed to halve the true residual
+        // (the fp64 floor of an ill-conditioned system: attainable accuracy reached).
+        const int fatal = !(rz > 0.0) || !(rr == rr) || k + 1 == P.maxit;
+        if (s_bad[b]) s_restarts[b] += 1;
+        s_stalls[b] = rr > 0.25 * s_lasttrue[b] ? s_stalls[b] + 1 : 0;
+        s_lasttrue[b] = rr;
+        if (conv || fatal || s_restarts[b] > 8 || s_stalls[b] >= 3) {
           s_state[b] = 2;
           fin = 1;
           if (cta == C_LO(b)) {
@@ -717,7 +889,7 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
           s_state[b] = 0;
           s_flush[b] = 1;                                  // x += y + alpha_k p_k rides on the next phase A
           s_maxr2[b] = rr;
-          s_beta[b] = rz / s_rzprev[b];
+          s_beta[b] = s_bad[b] ? 0.0 : rz / s_rzprev[b];   // restart after a breakdown: p = z
           s_rz[b] = rz;
         }
       }
@@ -755,10 +927,22 @@ __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(Mi
 #undef C_HI
 #undef OWN_RANGE
 #undef REDUCE_ALL
+#undef SYNC_REDUCE
 #undef TILE_RANGE
 #undef PIXEL_OF
 #undef PHASE_B_TILE
 }
+
+__global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(MixParams P) {
+  BandParams none;
+  pcg_ic_body<false>(P, none);
+}
+
+#ifndef IC_CG_BARRIER
+__global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_band_kernel(MixParams P, BandParams bp) {
+  pcg_ic_body<true>(P, bp);
+}
+#endif
 
 // two CTAs x (60 KB staged strips + 11 KB scalars + 1 KB reserved) = 144 KB -> the 164 KB shared-memory configuration, which
 // leaves 92 KB of L1 for phase A's stencil reuse (measured: below ~90 KB of L1 the matvec phase loses 35 %)
@@ -816,5 +1000,119 @@ int k_pcg_ic_launch(b200flow_ctx *ctx, MixParams P, int grid_max) {
   }
   return 0;
 }
+
+#ifndef IC_CG_BARRIER
+// ---- row-band mode: launcher, and the exchange of the solution bands after a solve ------------------------------------
+static BandParams make_band_params(const b200flow_ctx *ctx, int y0, int y1) {
+  BandParams bp;
+  memset(&bp, 0, sizeof bp);
+  const b200flow_band &bd = ctx->band;
+  bp.rank = bd.rank; bp.world = bd.world; bp.y0 = y0; bp.y1 = y1;
+  bp.self = reinterpret_cast<BandSync *>(bd.base[bd.rank]);
+  for (int r = 0; r < bd.world; ++r) bp.peer[r] = reinterpret_cast<BandSync *>(bd.base[r]);
+  return bp;
+}
+
+void band_rows(int H, int rank, int world, int *y0, int *y1) {
+  const int strips = (H + 7) / 8;                  // bands are whole 8-row strips: the IC sub-tiles never straddle a band
+  const int s0 = (int)((long long)strips * rank / world), s1 = (int)((long long)strips * (rank + 1) / world);
+  *y0 = s0 * 8;
+  *y1 = s1 * 8 < H ? s1 * 8 : H;
+}
+
+int k_pcg_ic_band_launch(b200flow_ctx *ctx, MixParams P, int grid_max) {
+  static_assert(sizeof(BandSync) <= B200FLOW_BAND_RESERVED, "BandSync must fit the reserved head of the arena block");
+  const LinSys &sys = P.sys;
+  if (sys.B != 1) return set_err(ctx, B200FLOW_EINVAL, "row-band mode solves one system at a time (B = %d)", sys.B);
+  const b200flow_band &bd = ctx->band;
+  int y0, y1;
+  band_rows(sys.H, bd.rank, bd.world, &y0, &y1);
+  BandParams bp = make_band_params(ctx, y0, y1);
+  int ty0, ty1;
+  if (bd.rank > 0) {                               // a neighbour exists only if its band is not empty
+    band_rows(sys.H, bd.rank - 1, bd.world, &ty0, &ty1);
+    if (ty1 > ty0) bp.up_delta = bd.base[bd.rank - 1] - bd.base[bd.rank];
+  }
+  if (bd.rank + 1 < bd.world) {
+    band_rows(sys.H, bd.rank + 1, bd.world, &ty0, &ty1);
+    if (ty1 > ty0) bp.dn_delta = bd.base[bd.rank + 1] - bd.base[bd.rank];
+  }
+  for (int r = 0; r < bd.world; ++r) {             // every band must be non-empty and start where the previous one ends
+    band_rows(sys.H, r, bd.world, &ty0, &ty1);
+    if (ty1 <= ty0) return set_err(ctx, B200FLOW_EINVAL, "row-band mode: %d rows do not split over %d ranks", sys.H, bd.world);
+  }
+  P.tiles_x = (int)cdiv(sys.W, 32);
+  P.tiles_y = (int)cdiv(y1 - y0, 8);
+  P.tiles_per_sys = P.tiles_x * P.tiles_y;
+  int G = grid_max;
+  if ((long long)G > P.tiles_per_sys) G = P.tiles_per_sys;
+  if (G < 1) G = 1;
+  P.w.grid = G;
+  P.debug = 0;
+  void *args[] = {&P, &bp};
+  if (ctx->plain_solver_launch) {                  // in-process emulation of several ranks on one GPU (tests): all grids must be co-resident
+    pcg_ic_band_kernel<<<dim3(G), dim3(IC_THREADS), IC_SMEM, ctx->stream>>>(P, bp);
+    BF_CUDA(ctx, cudaPeekAtLastError());
+  } else {
+    BF_CUDA(ctx, cudaLaunchCooperativeKernel((void *)pcg_ic_band_kernel, dim3(G), dim3(IC_THREADS), args, IC_SMEM, ctx->stream));
+  }
+  return 0;
+}
+
+// After a band solve every rank holds rows [y0, y1) of x: each rank stores its rows into every peer's x (same offset in the
+// peer's block) and the last CTA to finish runs one flag barrier, so that the kernel only completes once every peer's rows
+// have arrived here.
+__global__ void band_push_kernel(const double2 *__restrict__ x, long long first, long long count, BandParams bp,
+                                 unsigned *ticket) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += stride) {
+    const double2 v = x[first + i];
+    for (int r = 0; r < bp.world; ++r) {
+      if (r == bp.rank) continue;
+      double2 *dst = const_cast<double2 *>(band_shift(x + first + i, reinterpret_cast<const char *>(bp.peer[r]) -
+                                                                      reinterpret_cast<const char *>(bp.self)));
+      asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(v.x), "d"(v.y) : "memory");
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ unsigned last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *ticket = 0u;                                  // ready for the next push
+    BandSync *self = bp.self;
+    const unsigned long long seq = *(volatile unsigned long long *)&self->seq + 1ull;
+    __threadfence_system();
+    for (int r = 0; r < bp.world; ++r) st_release_sys_u64(&bp.peer[r]->flag[bp.rank], seq);
+    long long spins = 0;
+    for (int r = 0; r < bp.world; ++r)
+      while (ld_acquire_sys_u64(&self->flag[r]) < seq && ++spins < BAND_SPIN_LIMIT) {}
+    if (spins >= BAND_SPIN_LIMIT) self->error = seq;
+    self->seq = seq;
+    self->release = seq;
+    __threadfence_system();
+  }
+}
+
+int k_band_exchange_x(b200flow_ctx *ctx, double2 *x, int H, int W) {
+  const b200flow_band &bd = ctx->band;
+  int y0, y1;
+  band_rows(H, bd.rank, bd.world, &y0, &y1);
+  BandParams bp = make_band_params(ctx, y0, y1);
+  const long long count = (long long)(y1 - y0) * W;
+  int grid = (int)cdiv(count > 0 ? count : 1, 256 * 4);
+  if (grid > 4 * ctx->num_sms) grid = 4 * ctx->num_sms;
+  BF_LAUNCH(ctx, band_push_kernel, grid, 256, 0, x, (long long)y0 * W, count, bp, ctx->band.ticket);
+  return 0;
+}
+
+int k_band_error(b200flow_ctx *ctx, unsigned long long *err_host) {
+  BandSync *self = reinterpret_cast<BandSync *>(ctx->band.base[ctx->band.rank]);
+  BF_CUDA(ctx, cudaMemcpyAsync(err_host, &self->error, sizeof *err_host, cudaMemcpyDeviceToHost, ctx->stream));
+  BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+#endif
 
 }  // namespace bf

@@ -93,5 +93,8 @@ struct MixParams {
 // solve_ic.cu
 int pcg_ic_grid(b200flow_ctx *ctx, int *grid_out);
 int k_pcg_ic_launch(b200flow_ctx *ctx, MixParams P, int grid_max);
+int k_pcg_ic_band_launch(b200flow_ctx *ctx, MixParams P, int grid_max);   // row-band mode: this rank's rows of one system
+int k_band_exchange_x(b200flow_ctx *ctx, double2 *x, int H, int W);       // all-gather of the solution bands over P2P stores
+int k_band_error(b200flow_ctx *ctx, unsigned long long *err_host);
 
 }  // namespace bf

@@ -98,6 +98,10 @@ _SIGS = {
 _SIGS["b200flow_host_alloc"] = [C.c_ulonglong, C.POINTER(_vp)]
 _SIGS["b200flow_host_free"] = [_vp]
 _SIGS["b200flow_ctx_set_split"] = [C.c_int, C.c_int]
+_SIGS["b200flow_band_init"] = [C.c_int, C.c_int, C.c_ulonglong, C.c_int]
+_SIGS["b200flow_band_export"] = [_vp, C.POINTER(_vp)]
+_SIGS["b200flow_band_connect"] = [C.c_int, _vp, _vp]
+_SIGS["b200flow_band_close"] = []
 
 EXPORTS = sorted(list(_SIGS) + ["b200flow_abi_version", "b200flow_ctx_create", "b200flow_ctx_destroy",
                                 "b200flow_last_error", "b200flow_ctx_set_timing", "b200flow_ctx_sync",
