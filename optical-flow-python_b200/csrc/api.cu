@@ -5,6 +5,7 @@
 
 namespace bf {
 int k_band_error(b200flow_ctx *ctx, unsigned long long *err_host);
+int k_band_preload(b200flow_ctx *ctx);
 PenaltySet make_penalty_set(const b200flow_params *p, double alpha);
 int alloc_linsys(b200flow_ctx *ctx, int B, int H, int W, LinSys *s);
 }  // namespace bf
@@ -137,6 +138,7 @@ int b200flow_band_init(b200flow_ctx *ctx, int rank, int world, unsigned long lon
   ctx->band.base[rank] = p;
   ctx->band.ticket = reinterpret_cast<unsigned *>(p + B200FLOW_BAND_RESERVED / 2);
   if (const char *mp = getenv("B200FLOW_BAND_MIN_PIXELS")) ctx->band.min_pixels = atoll(mp);
+  BF_TRY(k_band_preload(ctx));
   if (same_device) {        // several ranks emulated on one GPU (tests): every rank's persistent solver must stay resident
     ctx->plain_solver_launch = true;
     ctx->solver_ctas_per_sm = 1;

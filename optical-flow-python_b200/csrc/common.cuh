@@ -164,6 +164,10 @@ inline int upload(b200flow_ctx *ctx, T **dev, const T *host, size_t count) {
 
 template <typename T>
 inline int download(b200flow_ctx *ctx, T *host, const T *dev, size_t count) {
+  // Row-band mode: a device->host copy into PAGEABLE memory waits inside the driver for the stream's kernels; when two ranks
+  // are emulated by two host threads of one process (tests), the other rank's launches then queue up behind that call while
+  // this rank's persistent solver spins on the other rank's arrival.  cudaStreamSynchronize waits without that side effect.
+  if (ctx->band.world > 1) BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   BF_CUDA(ctx, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }

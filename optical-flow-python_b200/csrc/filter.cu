@@ -3,6 +3,7 @@
 // sites (hs.py:96-97,139-140; ba.py:198-199), occlusion.py:6-56 and weighted_median.py:5-112.
 // Outputs of both medians are always one of the window's input samples, selected with compare/exchange
 // networks in registers (no arithmetic on the samples), so selections are bit-exact.
+#include <mutex>
 #include "kernels.cuh"
 
 namespace bf {
@@ -528,10 +529,20 @@ static int launch_wmedian(b200flow_ctx *ctx, const double2 *cand, const double2 
   int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
   size_t smem = (size_t)SW * SH * 6 * sizeof(double) + WM_WARPS * 32 * sizeof(double2);
   if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
-  BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // same shared-memory configuration as the persistent solver (solve_ic.cu IC_CARVEOUT_PCT): with concurrent sub-batches
-  // CTAs of both kernels share an SM, which they only can under one L1 / shared-memory split
-  BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributePreferredSharedMemoryCarveout, 64));
+  {
+    // function attributes once per process, device and window size (mutex-guarded): setting an attribute of a kernel that is
+    // running on another stream blocks the host until it ends, which would serialise concurrent sub-batches
+    static std::mutex mu;
+    static size_t smem_set[64] = {0};
+    std::lock_guard<std::mutex> lock(mu);
+    if (smem_set[ctx->device & 63] < smem) {
+      BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      // same shared-memory configuration as the persistent solver (solve_ic.cu IC_CARVEOUT_PCT): with concurrent
+      // sub-batches CTAs of both kernels share an SM, which they only can under one L1 / shared-memory split
+      BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributePreferredSharedMemoryCarveout, 64));
+      smem_set[ctx->device & 63] = smem;
+    }
+  }
   dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
   double inv2s2 = 1.0 / (2.0 * (sigma_i * sigma_i));
   BF_LAUNCH(ctx, (wmedian_kernel<NPL>), grd, WM_WARPS * 32, smem, cand, base, color, C, occ, H, W, hsz, inv2s2, out);

@@ -347,6 +347,12 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
             if (tm.on) cudaEventElapsedTime(&ms, tm.spans.back().a, tm.spans.back().b);
             int mn = 1 << 30, mx = 0; long long sum = 0;
             for (int b = 0; b < B; ++b) { int v = fl[1 + B + b]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; }
+            {
+              std::vector<double> rr(B);
+              cudaMemcpy(rr.data(), work.scal, sizeof(double) * B, cudaMemcpyDeviceToHost);
+              for (int b = 0; b < B; ++b)
+                if (fl[1 + b] != 1) fprintf(stderr, "[b200flow trace]   system %d NOT converged: status %d, relres %.3e after %d iterations\n", b, fl[1 + b], rr[b], fl[1 + B + b]);
+            }
             fprintf(stderr, "[b200flow trace] gnc %d level %d (%dx%d) warp %d: solve %.3f ms, iters min %d mean %.1f max %d, "
                             "%.1f us/iter(max), alg %.0f GB/s\n", ignc, l, h, w, it, ms, mn, (double)sum / B, mx,
                     mx ? 1e3 * ms / mx : 0.0, ms > 0 ? (double)sum * hw * pcg_bytes_per_pixel_iter(pcg_mode) / (ms * 1e6) : 0.0);
@@ -415,6 +421,7 @@ static int pipeline_finish(b200flow_ctx *ctx, PipelineRun *run, bool want, cudaE
   res->solver_bytes_per_pixel_iter = run->solver_bytes;
   for (int k = 0; k < B200FLOW_K_COUNT; ++k) { res->bytes[k] = run->tm.bytes[k]; res->calls[k] = run->tm.calls[k]; }
   if (want || ctx->timing) {
+    if (ctx->band.world > 1) BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // see download() in common.cuh
     BF_CUDA(ctx, cudaMemcpyAsync(res->hstats, run->dstats, sizeof res->hstats, cudaMemcpyDeviceToHost, ctx->stream));
     BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
