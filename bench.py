@@ -39,7 +39,7 @@ H, W = 480, 640
 # algorithmic bytes per pixel per PCG iteration (DESIGN.md section 4 / solve.cu headers):
 #   mixed (default): fp32 Krylov vectors + fp32 coefficient copy, phase A 76 B + phase B 44 B
 #   fp64           : every vector fp64, phase A 152 B + phase B 76 B
-PCG_BYTES = {"mixed": 128, "mixed-jacobi": 120, "fp64": 228}
+PCG_BYTES = {"mixed": 128, "mixed-jacobi": 120, "fp64": 228, "fp32": 128}
 PCG_KERNEL = {"mixed": "pcg_ic_kernel", "mixed-jacobi": "pcg_mixed_kernel", "fp64": "pcg_kernel"}
 PCG_PRECOND = {"mixed": "tile-local block-IC(0)", "mixed-jacobi": "block-Jacobi", "fp64": "block-Jacobi"}
 SAMPLE_H, SAMPLE_W = 120, 160         # CPU-baseline sample: centre crop with 1/16 of the pixels
@@ -306,8 +306,9 @@ def _timed_device_steps(ctx, P, B, d1, d2, duv, steps, warm, stream, torch):
 
 
 def run_variants(args, ctx, d1, d2, duv, B, local_rank, peak):
-    """The same workload with (i) the strict all-fp64 solver, (ii) the block-Jacobi mixed solver, (iii) two concurrent
-    sub-batches per GPU (b200flow_ctx_set_split): a few steps each, resident inputs, same timing method as `value`."""
+    """The same workload with (i) the strict all-fp64 solver, (ii) the fp32 variant (IC solver entirely in fp32, stopped at
+    1e-6 on its own residual: not parity-grade, statistical parity only), (iii) the block-Jacobi mixed solver, (iv) two
+    concurrent sub-batches per GPU (b200flow_ctx_set_split): a few steps each, resident inputs, timed like `value`."""
     import torch
     from optical_flow import _lib, load_of_method
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
@@ -321,7 +322,8 @@ def run_variants(args, ctx, d1, d2, duv, B, local_rank, peak):
         P = ope._c_params(levels=ope.pyramid_levels)
         ope._apply_solver(P)
         return P
-    for name, precision, split in (("fp64", "fp64", 1), ("mixed_jacobi", "mixed-jacobi", 1), ("concurrent_groups_2", "mixed", 2)):
+    for name, precision, split in (("fp64", "fp64", 1), ("fp32", "fp32", 1), ("mixed_jacobi", "mixed-jacobi", 1),
+                                   ("concurrent_groups_2", "mixed", 2)):
         if precision == args.solver_precision and split == (args.split or 1):
             continue
         try:

@@ -48,8 +48,12 @@ enum { B200FLOW_SOLVER_EXACT = 0,   /* replaces 'backslash' (spsolve): block-Jac
        B200FLOW_SOLVER_EXACT_F64 = 2, /* as EXACT with every vector in fp64 (the round-1 kernel; reported variant) */
        B200FLOW_SOLVER_SOR = 3,     /* the reference's legacy 'sor' (base.py:138-172): lexicographic SOR, omega 1.9, from
                                        x = 0 until ||x - x_old|| < tol ||x|| (tol 1e-2) or maxit (sor_max_iters) sweeps */
-       B200FLOW_SOLVER_EXACT_IC = 4 }; /* as EXACT (same fp64 true-residual criterion) preconditioned by a tile-local
+       B200FLOW_SOLVER_EXACT_IC = 4, /* as EXACT (same fp64 true-residual criterion) preconditioned by a tile-local
                                        2x2-block incomplete Cholesky IC(0) instead of block Jacobi: ~2.2x fewer iterations */
+       B200FLOW_SOLVER_FP32_IC = 5 };  /* the fp32 VARIANT: the IC-preconditioned solver run entirely in fp32 (Krylov vectors and
+                                       the solution increments; no fp64 residual replacement), stopped when the ITERATED fp32
+                                       residual reaches tol (1e-6 by default); the fp64 true residual is only reported.  Not
+                                       parity-grade: judged statistically, reported as a variant */
 
 /* Mirrors the public attributes of HSOpticalFlow / BAOpticalFlow / ClassicNLOpticalFlow
  * (methods/base.py:21-63, hs.py:23-47, ba.py:26-55, classic_nl.py:32-87; presets methods/config.py:10-176). */

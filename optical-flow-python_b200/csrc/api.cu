@@ -543,7 +543,7 @@ int b200flow_solve_increment_mc(b200flow_ctx *ctx, const b200flow_params *p, dou
   LinSys sys;
   BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, NC, &sys));
   if (!(p->tol > 0.0) || p->maxit < 1) return set_err(ctx, B200FLOW_EINVAL, "solver tol/maxit invalid");
-  if (p->solver < B200FLOW_SOLVER_EXACT || p->solver > B200FLOW_SOLVER_EXACT_IC)
+  if (p->solver < B200FLOW_SOLVER_EXACT || p->solver > B200FLOW_SOLVER_FP32_IC)
     return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
   size_t N = (size_t)H * W;
   PcgWork w;

@@ -76,10 +76,13 @@ enum { PCG_MODE_MIXED = 0,        // block-Jacobi PCG, fp32 Krylov vectors + fp6
        PCG_MODE_JACOBI_F64 = 1,   // scalar-Jacobi all-fp64 PCG: the reference's own 'pcg' mode (B200FLOW_SOLVER_PCG)
        PCG_MODE_BLOCK_F64 = 2,    // block-Jacobi all-fp64 PCG (B200FLOW_SOLVER_EXACT_F64)
        PCG_MODE_SOR = 3,          // the reference's legacy lexicographic SOR, omega 1.9 (B200FLOW_SOLVER_SOR)
-       PCG_MODE_MIXED_IC = 4 };   // as MIXED with the tile-local block-IC(0) preconditioner (B200FLOW_SOLVER_EXACT_IC)
+       PCG_MODE_MIXED_IC = 4,     // as MIXED with the tile-local block-IC(0) preconditioner (B200FLOW_SOLVER_EXACT_IC)
+       PCG_MODE_FP32_IC = 5 };    // the IC kernel without reliable updates, stopped on the iterated fp32 residual (B200FLOW_SOLVER_FP32_IC)
 inline int pcg_mode_of(int solver) { return solver; }
 // algorithmic bytes per pixel-iteration of a solver mode (roofline accounting; solve.cu / solve_ic.cu headers)
-inline int pcg_bytes_per_pixel_iter(int mode) { return mode == PCG_MODE_MIXED_IC ? 128 : mode == PCG_MODE_MIXED ? 120 : 228; }
+inline int pcg_bytes_per_pixel_iter(int mode) {
+  return (mode == PCG_MODE_MIXED_IC || mode == PCG_MODE_FP32_IC) ? 128 : mode == PCG_MODE_MIXED ? 120 : 228;
+}
 int k_pcg_solve(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                 int *iters_host /*[B] or null*/, double *relres_host /*[B] or null*/, bool sync_results);
 int k_pcg_solve_async(b200flow_ctx *, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,

@@ -114,7 +114,7 @@ int check_params(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
   if (B < 1 || H < 1 || W < 1) return set_err(ctx, B200FLOW_EINVAL, "bad batch/size B=%d H=%d W=%d", B, H, W);
   if (p->method < 0 || p->method > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown method %d", p->method);
   if (p->interp < 0 || p->interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", p->interp);
-  if (p->solver < B200FLOW_SOLVER_EXACT || p->solver > B200FLOW_SOLVER_EXACT_IC)
+  if (p->solver < B200FLOW_SOLVER_EXACT || p->solver > B200FLOW_SOLVER_FP32_IC)
     return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
   if (!(p->pyramid_spacing > 1.0) || p->pyramid_spacing > 8.0)
     return set_err(ctx, B200FLOW_EINVAL, "pyramid_spacing %g out of range (1, 8]", p->pyramid_spacing);
@@ -496,7 +496,7 @@ int run_pipeline(b200flow_ctx *ctx, const b200flow_params *p, int B, int H, int 
                  const double *color_planar, const double2 *init, double2 *uv_out, b200flow_stats *stats) {
   int ns = ctx->nsplit < 1 ? 1 : ctx->nsplit;
   if (ns > B) ns = B;
-  if (p && p->solver != B200FLOW_SOLVER_EXACT_IC) ns = 1;     // only pcg_ic_kernel is sized for co-residency
+  if (p && p->solver != B200FLOW_SOLVER_EXACT_IC && p->solver != B200FLOW_SOLVER_FP32_IC) ns = 1;     // only pcg_ic_kernel is sized for co-residency
   if (getenv("B200FLOW_TRACE")) ns = 1;
   std::vector<RunResult> rr(ns);
   if (ns == 1) {

@@ -867,7 +867,7 @@ int pcg_work_alloc(b200flow_ctx *ctx, int B, int H, int W, PcgWork *w) {
 
 int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol, int maxit, int mode,
                 int *iters_host, double *relres_host, bool sync_results) {
-  const bool mixed = mode == PCG_MODE_MIXED || mode == PCG_MODE_MIXED_IC;
+  const bool mixed = mode == PCG_MODE_MIXED || mode == PCG_MODE_MIXED_IC || mode == PCG_MODE_FP32_IC;
   const int tiles_x = (int)cdiv(sys.W, TILE_W), tiles_y = (int)cdiv(sys.H, TILE_H);
   const int tiles_per_sys = tiles_x * tiles_y;
   const long long total_tiles = (long long)tiles_per_sys * sys.B;
@@ -888,6 +888,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     P.tol2 = tol * tol;
     {
       double delta = mode == PCG_MODE_MIXED_IC ? PCG_RELIABLE_DELTA_IC : PCG_RELIABLE_DELTA;
+      if (mode == PCG_MODE_FP32_IC) delta = 0.0;             // no residual replacement on the way
 #ifdef B200FLOW_TUNING                                        // tuning builds only (scripts/build_variant.sh ... -DB200FLOW_TUNING)
       if (const char *dl = getenv("B200FLOW_RELIABLE_DELTA")) delta = atof(dl);
 #endif
@@ -896,6 +897,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     P.maxit = maxit;
     P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.tiles_per_sys = tiles_per_sys;
     P.debug = 0;
+    P.fp32_only = mode == PCG_MODE_FP32_IC;
     P.w.grid = G;
     // the fp32 working set (76 B / pixel) is carved out of the five fp64 vectors (80 B / pixel) of the work area
     const size_t n = (size_t)sys.B * sys.H * sys.W;
@@ -904,6 +906,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
     P.m.Ap = reinterpret_cast<float2 *>(w.p2); P.m.y = P.m.Ap + n;
     P.m.D = reinterpret_cast<float2 *>(w.z);   P.m.WH = P.m.D + n;
     P.m.WV = reinterpret_cast<float2 *>(w.Ap); P.m.a12 = reinterpret_cast<float *>(P.m.WV + n);
+    const bool ic = mode == PCG_MODE_MIXED_IC || mode == PCG_MODE_FP32_IC;
     if (mode == PCG_MODE_MIXED_IC && ctx->band.world > 1 && sys.B == 1 &&
         (long long)sys.H * sys.W >= ctx->band.min_pixels && (sys.H + 7) / 8 >= ctx->band.world) {
       // row-band mode: this rank iterates on its rows only, then the solution bands are exchanged (solve_ic.cu)
@@ -911,7 +914,7 @@ int k_pcg_solve(b200flow_ctx *ctx, LinSys sys, PcgWork w, double2 *x, double tol
       ctx->launches++;
       BF_TRY(k_band_exchange_x(ctx, x, sys.H, sys.W));
       ctx->launches--;                 // (the common exit below counts the solver launch)
-    } else if (mode == PCG_MODE_MIXED_IC) {
+    } else if (ic) {
       BF_TRY(k_pcg_ic_launch(ctx, P, w.grid_ic));
     } else {
       void *args[] = {&P};

@@ -303,6 +303,14 @@ __device__ __forceinline__ void st_sys_f64(double *p, double v) { asm volatile("
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -371,10 +379,11 @@ __device__ __forceinline__ void band_barrier_reduce(const BandParams &bp, unsign
         st_sys_f64(&bp.peer[r]->xs[slot][bp.rank][0], va);
         st_sys_f64(&bp.peer[r]->xs[slot][bp.rank][1], vb);
       }
-      __threadfence_system();                       // the band's vectors and the sums, before the flag
-      for (int r = 0; r < bp.world; ++r) st_release_sys_u64(&bp.peer[r]->flag[bp.rank], seq);
+      __threadfence_system();                       // ONE release fence: the band's vectors and the sums, before the flags
+      for (int r = 0; r < bp.world; ++r) st_relaxed_sys_u64(&bp.peer[r]->flag[bp.rank], seq);
       for (int r = 0; r < bp.world; ++r)
-        while (ld_acquire_sys_u64(&self->flag[r]) < seq && ++spins < limit) {}
+        while (ld_relaxed_sys_u64(&self->flag[r]) < seq && ++spins < limit) {}
+      __threadfence_system();                       // ONE acquire fence after all the flags have been seen
       double sa = 0.0, sb = 0.0;
       for (int r = 0; r < bp.world; ++r) { sa += ld_sys_f64(&self->xs[slot][r][0]); sb += ld_sys_f64(&self->xs[slot][r][1]); }
 #ifdef BAND_DEBUG
@@ -876,6 +885,9 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
         const int b = tid;
         double rz = s_ta[b], rr = s_tb[b];
         int conv = rr <= P.tol2 * s_bb[b];
+        // fp32 variant: the iterated fp32 residual has reached its target (that is what brought us here, unless it was a
+        // breakdown or the iteration cap); the fp64 residual just computed is reported, not enforced
+        if (P.fp32_only && !s_bad[b] && k + 1 < P.maxit && rr == rr) conv = 1;
         // An fp32 breakdown (p.Ap <= 0, r.z <= 0: the iterated quantities have lost their meaning close to the fp32
         // floor) is not the end: the fp64 residual and z = M^-1 r just computed are sound, so CG RESTARTS from them
         // (beta = 0).  Given up after 8 restarts, or when three replacements in a row failed to halve the true residual
@@ -1109,10 +1121,11 @@ __global__ void band_push_kernel(const double2 *__restrict__ x, long long first,
     BandSync *self = bp.self;
     const unsigned long long seq = *(volatile unsigned long long *)&self->seq + 1ull;
     __threadfence_system();
-    for (int r = 0; r < bp.world; ++r) st_release_sys_u64(&bp.peer[r]->flag[bp.rank], seq);
+    for (int r = 0; r < bp.world; ++r) st_relaxed_sys_u64(&bp.peer[r]->flag[bp.rank], seq);
     long long spins = 0;
     for (int r = 0; r < bp.world; ++r)
-      while (ld_acquire_sys_u64(&self->flag[r]) < seq && ++spins < BAND_SPIN_LIMIT) {}
+      while (ld_relaxed_sys_u64(&self->flag[r]) < seq && ++spins < BAND_SPIN_LIMIT) {}
+    __threadfence_system();
     if (spins >= BAND_SPIN_LIMIT) self->error = seq;
     self->seq = seq;
     self->release = seq;

@@ -88,6 +88,7 @@ struct MixParams {
   int maxit;
   int tiles_x, tiles_y, tiles_per_sys;
   int debug;                     // tuning builds (-DB200FLOW_TUNING) only; always 0 on the product path
+  int fp32_only;                 // fp32 variant: no residual replacement, convergence on the iterated fp32 residual
 };
 
 // solve_ic.cu

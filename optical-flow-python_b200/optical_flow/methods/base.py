@@ -12,7 +12,10 @@ The public attributes, their defaults and `parse_input_parameter` are those of t
                               is still declared on the fp64 residual ||b - A x|| <= exact_rtol ||b||; 'fp64': every
                               vector in fp64 (same criterion, 1.9x the memory traffic).  'mixed' is preconditioned by a
                               tile-local 2x2-block incomplete Cholesky IC(0) (~2.2x fewer iterations than block Jacobi);
-                              'mixed-jacobi' keeps the round-1 block-Jacobi preconditioner (reported variant)
+                              'mixed-jacobi' keeps the round-1 block-Jacobi preconditioner (reported variant);
+                              'fp32': the fp32 VARIANT north_star asks for -- the IC solver entirely in fp32, stopped when
+                              its own fp32 residual reaches fp32_rtol (1e-6), no fp64 residual replacement; everything
+                              else stays fp64.  Not parity-grade (judged statistically, tests/test_gpu_fp32_variant.py)
   last_stats                  dict of solver / launch statistics of the most recent compute_flow call
 """
 import copy
@@ -23,7 +26,7 @@ import numpy as np
 from optical_flow import _lib
 
 # solver_precision -> B200FLOW_SOLVER_* of the 'backslash' stand-in (include/b200flow.h)
-_EXACT_SOLVERS = {'mixed': 4, 'mixed-jacobi': 0, 'fp64': 2}
+_EXACT_SOLVERS = {'mixed': 4, 'mixed-jacobi': 0, 'fp64': 2, 'fp32': 5}
 from optical_flow.robust.robust_function import RobustFunction
 from optical_flow.utils.derivatives import INTERP_CODES
 from optical_flow.utils.image_processing import fspecial_gaussian
@@ -162,6 +165,7 @@ class BaseOpticalFlow(ABC):
         self.exact_rtol = 1e-12
         self.exact_maxiter = 20000
         self.solver_precision = 'mixed'
+        self.fp32_rtol = 1e-6
         self.last_stats = None
 
     def parse_input_parameter(self, params):
@@ -189,6 +193,8 @@ class BaseOpticalFlow(ABC):
             if prec not in _EXACT_SOLVERS:
                 raise ValueError(f"Unknown solver_precision: {self.solver_precision}")
             P.solver, P.tol, P.maxit = _EXACT_SOLVERS[prec], float(self.exact_rtol), int(self.exact_maxiter)
+            if prec == 'fp32':          # the fp32 variant stops on its own (iterated) residual: fp32 cannot deliver 1e-12
+                P.tol = float(self.fp32_rtol)
         elif solver == 'pcg':
             P.solver, P.tol, P.maxit = 1, float(self.pcg_rtol), int(self.pcg_maxiter)
         elif solver == 'sor':      # base.py:109-110: _sor_solve(A, b, 1.9, self.sor_max_iters, 1e-2)
