@@ -3,6 +3,8 @@
 // pyramid.py:6-73, warping.py:6-45 of the reference.  All kernels are one-thread-per-output-element
 // streaming stencils (HBM-bound, coalesced along W); compiled with -fmad=false so that the integer-valued
 // decisions (gray quantisation, resize sample indices) round exactly like the NumPy reference.
+#include <cuda.h>
+#include <mutex>
 #include "kernels.cuh"
 
 namespace bf {
@@ -136,6 +138,19 @@ __device__ __forceinline__ double rof_div(const double2 *__restrict__ p, int y, 
   return dx + dy;
 }
 
+// reprojection p /= max(1, |p|) (image_processing.py:118-122).  |p| <= 1 leaves p untouched (dividing by 1.0 is exact); the
+// other branch multiplies by rsqrt(|p|^2) instead of sqrt + two divides: the dual iteration is fp64-pipe bound on the tiled
+// kernel and the divides were half of its arithmetic.  <= 2 ulp from the reference's rounding, contractive iteration: the
+// texture image agrees with the reference's to 1e-12 (tests: ROF goldens at 7 and 100 iterations, tolerance 1e-9).
+__device__ __forceinline__ void rof_project(double2 &p) {
+  const double n2 = p.x * p.x + p.y * p.y;
+  if (n2 > 1.0) {
+    const double r = rsqrt(n2);
+    p.x = p.x * r;
+    p.y = p.y * r;
+  }
+}
+
 __global__ void rof_iter_kernel(const double *__restrict__ im, const double2 *__restrict__ pin,
                                 double2 *__restrict__ pout, int H, int W, double theta, double delta) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,9 +166,7 @@ __global__ void rof_iter_kernel(const double *__restrict__ im, const double2 *__
   double2 p = pin[i];
   p.x = p.x + delta * gx;
   p.y = p.y + delta * gy;
-  double nrm = fmax(sqrt(p.x * p.x + p.y * p.y), 1.0);
-  p.x = p.x / nrm;
-  p.y = p.y / nrm;
+  rof_project(p);
   pout[i] = p;
 }
 
@@ -166,6 +179,126 @@ __global__ void rof_finish_kernel(const double *__restrict__ im, const double2 *
   long long i = (long long)y * W + x;
   double s = im[off + i] + theta * rof_div(p + off, y, x, W);
   out[off + i] = im[off + i] - alp * s;
+}
+
+// ---- ROF on shared-memory tiles, RT_K dual iterations per launch (temporal blocking), tiles loaded by TMA ---------------
+// A CTA loads the (RT_TW + 2 RT_K) x (RT_TH + 2 RT_K) neighbourhood of its RT_TW x RT_TH output tile -- the normalised image and
+// the dual field p -- with two cp.async.bulk.tensor loads (one elected thread, completion on an mbarrier), runs RT_K
+// iterations on the tile in shared memory (the region that is still exact shrinks by one pixel per iteration), and writes
+// the interior of p.  The TMA unit zero-fills everything outside the image, which IS the reference's boundary rule for p
+// (div p at the first column / row uses p itself = p - 0); the forward differences of u are switched off at the last
+// column / row by global coordinates.  Arithmetic is operation-for-operation that of rof_iter_kernel (bit-identical
+// results); HBM traffic per pixel and iteration drops from 40 B to (24 x 1.69 + 16) / RT_K = 14 B.
+// Every thread keeps a fixed set of seven staged pixels for all iterations (no index arithmetic in the loop, seven independent
+// dependency chains).  Measured (B200, 32 planes of 640x480): see DESIGN.md section 4 -- the kernel is bound by the fp64
+// pipe, not by HBM, which is why a version that marched down columns to evaluate u once per pixel (fewer operations, but a
+// serial chain per warp) was slower.
+// Needs an even image width (TMA row pitch must be a multiple of 16 bytes); other widths keep rof_iter_kernel.
+constexpr int RT_K = 4, RT_TW = 64, RT_TH = 16, RT_BW = RT_TW + 2 * RT_K, RT_BH = RT_TH + 2 * RT_K, RT_N = RT_BW * RT_BH;
+constexpr int RT_THREADS = 256;
+constexpr size_t RT_SMEM = 128 + (size_t)RT_N * (sizeof(double) + 2 * sizeof(double2));   // image + two copies of p (ping-pong)
+
+__device__ __forceinline__ double rof_div_s(const double2 *sp, int l) {   // l = ly * RT_BW + lx, all four neighbours staged
+  const double2 c = sp[l];
+  return (c.x - sp[l - 1].x) + (c.y - sp[l - RT_BW].y);
+}
+
+__global__ void __launch_bounds__(RT_THREADS, 3) rof_tile_kernel(const __grid_constant__ CUtensorMap tm_im,
+                                                                 const __grid_constant__ CUtensorMap tm_p,
+                                                                 double2 *__restrict__ pout, int H, int W, double theta,
+                                                                 double delta, int iters) {
+  extern __shared__ unsigned char rt_raw[];
+  unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(rt_raw) + 127) & ~uintptr_t(127));
+  double *s_im = reinterpret_cast<double *>(base);                                    // [RT_BH][RT_BW]
+  double2 *s_p0 = reinterpret_cast<double2 *>(base + (size_t)RT_N * sizeof(double));  // [RT_BH][RT_BW] (x, y) interleaved
+  double2 *s_p1 = s_p0 + RT_N;
+  __shared__ __align__(8) unsigned long long bar;
+  const int x0 = blockIdx.x * RT_TW - RT_K, y0 = blockIdx.y * RT_TH - RT_K, plane = blockIdx.z;
+  const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // make the initialised barrier visible to the TMA unit
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)(RT_N * (sizeof(double) + sizeof(double2)));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    // coordinates innermost first; anything outside [0, W) x [0, H) arrives as zeros
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(s_im)), "l"(reinterpret_cast<unsigned long long>(&tm_im)), "r"(x0), "r"(y0),
+                   "r"(plane), "r"(bar_a) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(s_p0)), "l"(reinterpret_cast<unsigned long long>(&tm_p)), "r"(2 * x0), "r"(y0),
+                   "r"(plane), "r"(bar_a) : "memory");
+  }
+  {
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar_a) : "memory");
+  }
+  double2 *src = s_p0, *dst = s_p1;
+  constexpr int NPX = (RT_N + RT_THREADS - 1) / RT_THREADS;      // 7 staged pixels per thread
+  int lxs[NPX], lys[NPX];
+#pragma unroll
+  for (int i = 0; i < NPX; ++i) {
+    const int idx = threadIdx.x + i * RT_THREADS;
+    lys[i] = idx < RT_N ? idx / RT_BW : -100;                     // a slot past the tile never passes the region test
+    lxs[i] = idx - (idx / RT_BW) * RT_BW;
+  }
+  for (int j = 0; j < iters; ++j) {
+    const int m = j + 1;
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+      const int lx = lxs[i], ly = lys[i];
+      if (lx < m || lx >= RT_BW - m || ly < m || ly >= RT_BH - m) continue;
+      const int gx_ = x0 + lx, gy_ = y0 + ly, l = ly * RT_BW + lx;
+      double2 p = make_double2(0.0, 0.0);
+      if (gx_ >= 0 && gx_ < W && gy_ >= 0 && gy_ < H) {
+        const double u = s_im[l] + theta * rof_div_s(src, l);
+        double gx = 0.0, gy = 0.0;
+        if (gx_ < W - 1) gx = (s_im[l + 1] + theta * rof_div_s(src, l + 1)) - u;
+        if (gy_ < H - 1) gy = (s_im[l + RT_BW] + theta * rof_div_s(src, l + RT_BW)) - u;
+        p = src[l];
+        p.x = p.x + delta * gx;
+        p.y = p.y + delta * gy;
+        rof_project(p);
+      }
+      dst[l] = p;
+    }
+    __syncthreads();
+    double2 *t = src; src = dst; dst = t;
+  }
+  pout += (long long)plane * H * W;
+  for (int idx = threadIdx.x; idx < RT_TW * RT_TH; idx += RT_THREADS) {
+    const int ly = RT_K + idx / RT_TW, lx = RT_K + idx % RT_TW;
+    const int gx_ = x0 + lx, gy_ = y0 + ly;
+    if (gx_ < W && gy_ < H) pout[(long long)gy_ * W + gx_] = src[ly * RT_BW + lx];
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D tensor map over P planes of H rows of `row_doubles` doubles, box bw x bh x 1
+static int make_plane_map(b200flow_ctx *ctx, CUtensorMap *tm, const void *ptr, int P, int H, long long row_doubles, int bw, int bh) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    BF_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return set_err(ctx, B200FLOW_ECUDA, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)row_doubles, (cuuint64_t)H, (cuuint64_t)P};
+  cuuint64_t strides[2] = {(cuuint64_t)row_doubles * 8, (cuuint64_t)row_doubles * 8 * (cuuint64_t)H};
+  cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u}, estr[3] = {1u, 1u, 1u};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(ctx, B200FLOW_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
 }
 
 int k_rof_texture(b200flow_ctx *ctx, const double *img, double *out, int B, int C, int H, int W, double theta,
@@ -181,9 +314,37 @@ int k_rof_texture(b200flow_ctx *ctx, const double *img, double *out, int B, int 
   BF_CUDA(ctx, cudaMemsetAsync(pa, 0, sizeof(double2) * P * HW, ctx->stream));
   dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), P);
   double delta = 1.0 / (4.0 * theta);
-  for (int it = 0; it < iters; ++it) {
-    BF_LAUNCH(ctx, rof_iter_kernel, grd, blk, 0, norm, pa, pb, H, W, theta, delta);
-    std::swap(pa, pb);
+  const bool tiled = W % 2 == 0 && W >= 16 && H >= 8 && getenv("B200FLOW_ROF_SCALAR") == nullptr;
+  if (tiled) {
+    static std::mutex mu;
+    static bool attr_done[64] = {false};
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (!attr_done[ctx->device & 63]) {
+        BF_CUDA(ctx, cudaFuncSetAttribute(rof_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
+        BF_CUDA(ctx, cudaFuncSetAttribute(rof_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));      // three 69 KB tiles per SM
+        attr_done[ctx->device & 63] = true;
+      }
+    }
+    CUtensorMap tm_im, tm_pa, tm_pb;
+    BF_TRY(make_plane_map(ctx, &tm_im, norm, P, H, W, RT_BW, RT_BH));
+    BF_TRY(make_plane_map(ctx, &tm_pa, pa, P, H, 2LL * W, 2 * RT_BW, RT_BH));
+    BF_TRY(make_plane_map(ctx, &tm_pb, pb, P, H, 2LL * W, 2 * RT_BW, RT_BH));
+    dim3 tg((unsigned)cdiv(W, RT_TW), (unsigned)cdiv(H, RT_TH), P);
+    bool a_is_src = true;
+    for (int it = 0; it < iters; it += RT_K) {
+      const int n = iters - it < RT_K ? iters - it : RT_K;
+      BF_LAUNCH(ctx, rof_tile_kernel, tg, RT_THREADS, RT_SMEM, tm_im, a_is_src ? tm_pa : tm_pb, a_is_src ? pb : pa, H, W, theta,
+                delta, n);
+      a_is_src = !a_is_src;
+    }
+    if (!a_is_src) std::swap(pa, pb);           // pa = the latest p
+  } else {
+    for (int it = 0; it < iters; ++it) {
+      BF_LAUNCH(ctx, rof_iter_kernel, grd, blk, 0, norm, pa, pb, H, W, theta, delta);
+      std::swap(pa, pb);
+    }
   }
   BF_LAUNCH(ctx, rof_finish_kernel, grd, blk, 0, norm, pa, (double *)pb, H, W, theta, alp);
   BF_TRY(k_minmax_scale(ctx, (double *)pb, out, B, (long long)C * HW, 0.0, 255.0));
