@@ -58,7 +58,8 @@ int auto_levels(int H, int W, double spacing);
 // frames: [B][2*NC][H][W], NC channels of frame 1 then NC channels of frame 2 (bstride = 2*NC*H*W for a dense batch);
 // I1x / I1y / src2 / It / Ix / Iy are [B][NC][H][W]
 int k_level_prep(b200flow_ctx *, const double *frames, long long bstride, int B, int NC, int H, int W,
-                 int interp, const double filt[5], double *I1x, double *I1y, double4 *src2);
+                 int interp, const double filt[5], double *I1x, double *I1y, double4 *src2,
+                 double4 *tmp = nullptr /* [B][NC][H][W] scratch of the spline prefilter; allocated when null */);
 int k_warp_assemble(b200flow_ctx *, const double *frames, long long bstride, int NC, const double *I1x, const double *I1y,
                     const double4 *src2,
                     const double2 *uv, const double2 *duv, int B, int H, int W, int interp, double blend,

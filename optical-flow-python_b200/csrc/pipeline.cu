@@ -261,6 +261,8 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
   BF_TRY(arena_alloc(ctx, &I1x, NC * N));
   BF_TRY(arena_alloc(ctx, &I1y, NC * N));
   BF_TRY(arena_alloc(ctx, &src2, NC * N));
+  double4 *src2_tmp = nullptr;                            // out-of-place partner of the cubic-spline prefilter
+  if (p->interp == B200FLOW_INTERP_CUBIC) BF_TRY(arena_alloc(ctx, &src2_tmp, NC * N));
   BF_TRY(alloc_linsys(ctx, B, H, W, &sys));
   BF_TRY(pcg_work_alloc(ctx, B, H, W, &work));
   BF_TRY(arena_alloc(ctx, &dstats, 4));
@@ -309,7 +311,7 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
       ch = h; cw = w;
       // Hermite: read im1, im2 16, write I1x, I1y 16 + {Z, DX, DY, DXY} 32; spline: + two in-place prefilter passes of 32 B r/w
       TIMED(B200FLOW_K_LEVEL_PREP, (p->interp == B200FLOW_INTERP_CUBIC ? 64.0 + 128.0 : 64.0) * NC * npx,
-            k_level_prep(ctx, frames, bstride, B, NC, h, w, p->interp, p->deriv_filter, I1x, I1y, src2));
+            k_level_prep(ctx, frames, bstride, B, NC, h, w, p->interp, p->deriv_filter, I1x, I1y, src2, src2_tmp));
       sys.H = h; sys.W = w;
       if (hs) BF_LAUNCH(ctx, fill_int_kernel, (unsigned)cdiv(B, 128), 128, 0, active, B, 1);
       const int warps = hs ? p->max_warping_iters : p->max_iters;

@@ -127,80 +127,150 @@ __global__ void level_prep_kernel(const double *__restrict__ frames, long long b
   src2[i] = make_double4(im2[(long long)y * W + x], a2x, a2y, dxy);
 }
 
-// cubic B-spline prefilter, pole z = sqrt(3)-2, gain 6, whole-sample mirror boundary, in place on the three
-// live components of the double4 (scipy ni_splines.c apply_filter).  One thread per line.
+// cubic B-spline prefilter, pole z = sqrt(3)-2, gain 6, whole-sample mirror boundary, on the three live components of
+// the double4 (scipy ni_splines.c apply_filter): per line  c+_i = gain c_i + z c+_{i-1}  (causal, exact
+// mirror initialisation) then  c_i = z (c_{i+1} - c+_i)  (anticausal, exact end initialisation).
+// The recursions are sequential along a line, but |z| = 0.268 forgets its past at 2^-1.9 per sample: a line is cut into
+// SEGMENTS, and a segment that does not start at the line's end runs BSP_WARM = 64 samples of warm-up from a zero state
+// first (z^64 = 2e-37: what the truncation leaves is 20 orders below the last bit, so the result has the bits of the
+// whole-line recursion).  One thread per (line, segment), lines fastest across a warp: the column pass is coalesced and
+// the row pass touches exactly one 32-byte sector per thread and step; a 1080-row plane gives 1080 x 15 threads instead
+// of 1080.  Out of place (src -> dst) because warm-ups read samples other segments are overwriting.
+constexpr int BSP_SEG = 128, BSP_WARM = 64;
 __device__ __forceinline__ void d4_scale(double4 &v, double s) { v.x *= s; v.y *= s; v.z *= s; }
 
-__global__ void bspline_prefilter_kernel(double4 *__restrict__ c, int H, int W, int along_x, int nlines) {
-  int line = blockIdx.x * blockDim.x + threadIdx.x;
-  if (line >= nlines) return;
-  int n, stride;
-  long long base;
-  if (along_x) {            // lines are rows: line = plane*H + y
-    n = W; stride = 1; base = (long long)line * W;
-  } else {                  // lines are columns: line = plane*W + x
-    n = H; stride = W; base = (long long)(line / W) * H * W + (line % W);
-  }
-  if (n < 2) return;
+struct BspLine { long long base; int n, stride; };
+__device__ __forceinline__ bool bsp_line(int item, int H, int W, int along_x, int nlines, BspLine &L, int &seg) {
+  const int line = item % nlines;
+  seg = item / nlines;
+  if (along_x) { L.n = W; L.stride = 1; L.base = (long long)line * W; }                                   // line = plane * H + y
+  else { L.n = H; L.stride = W; L.base = (long long)(line / W) * H * W + (line % W); }                    // line = plane * W + x
+  return true;
+}
+
+__global__ void bspline_causal_kernel(const double4 *__restrict__ src, double4 *__restrict__ dst, int H, int W, int along_x,
+                                      int nlines, int nseg) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= nlines * nseg) return;
+  BspLine L; int seg;
+  bsp_line(item, H, W, along_x, nlines, L, seg);
+  const int n = L.n;
+  const long long st = L.stride;
+  const double4 *p = src + L.base;
+  double4 *q = dst + L.base;
+  if (n < 2) { if (seg == 0 && n == 1) q[0] = p[0]; return; }
   const double z = -0.2679491924311227064725536584941276330571947461896193719441930205;   // sqrt(3)-2
   const double gain = (1.0 - z) * (1.0 - 1.0 / z);
-  double4 *p = c + base;
-  // pass 0: gain + causal initialisation sum  c0 = [c0 + z^(n-1) c_{n-1} + sum_{i=1}^{n-2} z^i (c_i + z^(n-1) c_{n-1-i})] / (1 - z^(2n-2))
-  double zn1 = pow(z, (double)(n - 1));
-  double4 first = p[0], last = p[(long long)(n - 1) * stride];
-  d4_scale(first, gain);
-  d4_scale(last, gain);
-  double sx = first.x + zn1 * last.x, sy = first.y + zn1 * last.y, sz = first.z + zn1 * last.z;
-  double zi = z;
-  for (int i = 1; i < n - 1; ++i) {
-    double4 a = p[(long long)i * stride], b = p[(long long)(n - 1 - i) * stride];
-    sx += zi * (a.x * gain + zn1 * (b.x * gain));
-    sy += zi * (a.y * gain + zn1 * (b.y * gain));
-    sz += zi * (a.z * gain + zn1 * (b.z * gain));
-    zi *= z;
-    if (fabs(zi) < 1e-300 && zn1 == 0.0) break;   // remaining terms are exactly negligible
+  const int a = seg * BSP_SEG, b = (seg + 1 == nseg) ? n : (seg + 1) * BSP_SEG;
+  double4 prev;
+  int i0;
+  if (a == 0) {
+    // causal initialisation  c0 = [c0 + z^(n-1) c_{n-1} + sum_{i=1}^{n-2} z^i (c_i + z^(n-1) c_{n-1-i})] / (1 - z^(2n-2))
+    double zn1 = pow(z, (double)(n - 1));
+    double4 first = p[0], last = p[(long long)(n - 1) * st];
+    d4_scale(first, gain);
+    d4_scale(last, gain);
+    double sx = first.x + zn1 * last.x, sy = first.y + zn1 * last.y, sz = first.z + zn1 * last.z;
+    double zi = z;
+    for (int i = 1; i < n - 1; ++i) {
+      double4 u = p[(long long)i * st], v = p[(long long)(n - 1 - i) * st];
+      sx += zi * (u.x * gain + zn1 * (v.x * gain));
+      sy += zi * (u.y * gain + zn1 * (v.y * gain));
+      sz += zi * (u.z * gain + zn1 * (v.z * gain));
+      zi *= z;
+      if (fabs(zi) < 1e-40 && fabs(zn1) < 1e-40) break;   // what is left is 20 orders below the last bit of the sum
+    }
+    double den = 1.0 - zn1 * zn1;
+    prev = make_double4(sx / den, sy / den, sz / den, p[0].w);
+    q[0] = prev;
+    i0 = 1;
+  } else {
+    prev = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int i = a - BSP_WARM; i < a; ++i) {
+      const double4 v = p[(long long)i * st];
+      prev.x = v.x * gain + z * prev.x;
+      prev.y = v.y * gain + z * prev.y;
+      prev.z = v.z * gain + z * prev.z;
+    }
+    i0 = a;
   }
-  double den = 1.0 - zn1 * zn1;
-  double4 prev = make_double4(sx / den, sy / den, sz / den, 0.0);
-  p[0] = prev;
-  // pass 1: causal recursion c_i += z c_{i-1}  (input still unscaled for i >= 1)
-  for (int i = 1; i < n; ++i) {
-    double4 v = p[(long long)i * stride];
+  for (int i = i0; i < b; ++i) {
+    double4 v = p[(long long)i * st];
     v.x = v.x * gain + z * prev.x;
     v.y = v.y * gain + z * prev.y;
     v.z = v.z * gain + z * prev.z;
-    p[(long long)i * stride] = v;
-    prev = v;
-  }
-  // pass 2: anticausal initialisation and recursion c_i = z (c_{i+1} - c_i)
-  double4 pm = p[(long long)(n - 2) * stride];
-  double k = z / (z * z - 1.0);
-  prev.x = (z * pm.x + prev.x) * k;
-  prev.y = (z * pm.y + prev.y) * k;
-  prev.z = (z * pm.z + prev.z) * k;
-  p[(long long)(n - 1) * stride] = prev;
-  for (int i = n - 2; i >= 0; --i) {
-    double4 v = p[(long long)i * stride];
-    v.x = z * (prev.x - v.x);
-    v.y = z * (prev.y - v.y);
-    v.z = z * (prev.z - v.z);
-    p[(long long)i * stride] = v;
+    q[(long long)i * st] = v;
     prev = v;
   }
 }
 
+__global__ void bspline_anticausal_kernel(const double4 *__restrict__ src, double4 *__restrict__ dst, int H, int W,
+                                          int along_x, int nlines, int nseg) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= nlines * nseg) return;
+  BspLine L; int seg;
+  bsp_line(item, H, W, along_x, nlines, L, seg);
+  const int n = L.n;
+  const long long st = L.stride;
+  const double4 *p = src + L.base;            // the causal pass' output c+
+  double4 *q = dst + L.base;
+  if (n < 2) { if (seg == 0 && n == 1) q[0] = p[0]; return; }
+  const double z = -0.2679491924311227064725536584941276330571947461896193719441930205;
+  const int a = seg * BSP_SEG, b = (seg + 1 == nseg) ? n : (seg + 1) * BSP_SEG;
+  double4 prev;
+  int i1;                                     // first index (going down) that is stored
+  if (b + BSP_WARM >= n) {
+    // anticausal initialisation at the line's end, then down to this segment (at most BSP_WARM + BSP_SEG unsaved steps)
+    const double4 pm = p[(long long)(n - 2) * st], pl = p[(long long)(n - 1) * st];
+    const double k = z / (z * z - 1.0);
+    prev = make_double4((z * pm.x + pl.x) * k, (z * pm.y + pl.y) * k, (z * pm.z + pl.z) * k, pl.w);
+    if (b == n) q[(long long)(n - 1) * st] = prev;
+    for (int i = n - 2; i >= b; --i) {
+      const double4 v = p[(long long)i * st];
+      prev.x = z * (prev.x - v.x); prev.y = z * (prev.y - v.y); prev.z = z * (prev.z - v.z);
+    }
+    i1 = b == n ? n - 2 : b - 1;
+  } else {
+    prev = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int i = b + BSP_WARM - 1; i >= b; --i) {
+      const double4 v = p[(long long)i * st];
+      prev.x = z * (prev.x - v.x); prev.y = z * (prev.y - v.y); prev.z = z * (prev.z - v.z);
+    }
+    i1 = b - 1;
+  }
+  for (int i = i1; i >= a; --i) {
+    double4 v = p[(long long)i * st];
+    v.x = z * (prev.x - v.x);
+    v.y = z * (prev.y - v.y);
+    v.z = z * (prev.z - v.z);
+    q[(long long)i * st] = v;
+    prev = v;
+  }
+}
+
+static int bspline_prefilter_axis(b200flow_ctx *ctx, double4 *c, double4 *tmp, int planes, int H, int W, int along_x) {
+  const int n = along_x ? W : H, nlines = planes * (along_x ? H : W);
+  int nseg = n / BSP_SEG;                       // the last segment takes the remainder; short lines are one exact segment
+  if (nseg < 1) nseg = 1;
+  const long long items = (long long)nlines * nseg;
+  BF_LAUNCH(ctx, bspline_causal_kernel, (unsigned)cdiv(items, 128), 128, 0, c, tmp, H, W, along_x, nlines, nseg);
+  BF_LAUNCH(ctx, bspline_anticausal_kernel, (unsigned)cdiv(items, 128), 128, 0, tmp, c, H, W, along_x, nlines, nseg);
+  return 0;
+}
+
 int k_level_prep(b200flow_ctx *ctx, const double *frames, long long bstride, int B, int NC, int H, int W,
-                 int interp, const double filt[5], double *I1x, double *I1y, double4 *src2) {
+                 int interp, const double filt[5], double *I1x, double *I1y, double4 *src2, double4 *tmp) {
   Filt5 f;
   for (int i = 0; i < 5; ++i) f.h[i] = filt[i];
   dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B * NC);
   BF_LAUNCH(ctx, level_prep_kernel, grd, blk, 0, frames, bstride, NC, H, W,
             interp == B200FLOW_INTERP_BICUBIC ? 1 : 0, f, I1x, I1y, src2);
   if (interp == B200FLOW_INTERP_CUBIC) {
-    // scipy spline_filter: axis 0 (columns) first, then axis 1 (rows)
-    int ncol = B * NC * W, nrow = B * NC * H;
-    BF_LAUNCH(ctx, bspline_prefilter_kernel, (unsigned)cdiv(ncol, 64), 64, 0, src2, H, W, 0, ncol);
-    BF_LAUNCH(ctx, bspline_prefilter_kernel, (unsigned)cdiv(nrow, 64), 64, 0, src2, H, W, 1, nrow);
+    // scipy spline_filter: axis 0 (columns) first, then axis 1 (rows); tmp: the out-of-place partner of src2
+    double4 *t = tmp;
+    if (!t) BF_TRY(arena_alloc(ctx, &t, (size_t)B * NC * H * W));
+    BF_TRY(bspline_prefilter_axis(ctx, src2, t, B * NC, H, W, 0));
+    BF_TRY(bspline_prefilter_axis(ctx, src2, t, B * NC, H, W, 1));
   }
   return 0;
 }
