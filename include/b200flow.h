@@ -224,6 +224,11 @@ int b200flow_operator_apply_mc(b200flow_ctx*, const b200flow_params*, double alp
 int b200flow_solve_increment_mc(b200flow_ctx*, const b200flow_params*, double alpha, const double *uv, const double *duv,
                                 const double *It, const double *Ix, const double *Iy, int H, int W, int NC,
                                 double *x, int *iters, double *relres);
+/* as solve_increment_mc with the caller's own right-hand side rhs (H,W,2) instead of the assembled b: the reference's
+ * _solve_linear_system(A, b, uv_shape) accepts any b (methods/base.py:87-114) */
+int b200flow_solve_rhs_mc(b200flow_ctx*, const b200flow_params *p, double alpha, const double *uv, const double *duv,
+                          const double *It, const double *Ix, const double *Iy, int H, int W, int NC, const double *rhs,
+                          double *x, int *iters, double *relres);
 int b200flow_detect_occlusion_mc(b200flow_ctx*, const double *uv, const double *images, int H, int W, int NC,
                                  double sigma_d, double sigma_i, double *occ);
 

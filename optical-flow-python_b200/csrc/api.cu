@@ -557,6 +557,30 @@ int b200flow_solve_increment_mc(b200flow_ctx *ctx, const b200flow_params *p, dou
   return rc;
 }
 
+// the reference's _solve_linear_system(A, b, uv_shape) takes ANY right-hand side (base.py:87-114): same system, caller's b
+int b200flow_solve_rhs_mc(b200flow_ctx *ctx, const b200flow_params *p, double alpha, const double *uv, const double *duv,
+                          const double *It, const double *Ix, const double *Iy, int H, int W, int NC, const double *rhs,
+                          double *x, int *iters, double *relres) {
+  API_BEGIN(ctx);
+  if (!rhs) return set_err(ctx, B200FLOW_EINVAL, "rhs is NULL");
+  LinSys sys;
+  BF_TRY(assemble_host(ctx, p, alpha, uv, duv, It, Ix, Iy, H, W, NC, &sys));
+  if (!(p->tol > 0.0) || p->maxit < 1) return set_err(ctx, B200FLOW_EINVAL, "solver tol/maxit invalid");
+  if (p->solver < B200FLOW_SOLVER_EXACT || p->solver > B200FLOW_SOLVER_FP32_IC)
+    return set_err(ctx, B200FLOW_EINVAL, "Unknown solver: %d", p->solver);
+  size_t N = (size_t)H * W;
+  BF_CUDA(ctx, cudaMemcpyAsync(sys.rhs, rhs, 2 * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));   // after the assembly
+  PcgWork w;
+  double2 *d_x;
+  BF_TRY(pcg_work_alloc(ctx, 1, H, W, &w));
+  BF_TRY(arena_alloc(ctx, &d_x, N));
+  int rc = k_pcg_solve(ctx, sys, w, d_x, p->tol, p->maxit, pcg_mode_of(p->solver), iters, relres, true);
+  if (rc < 0 && rc != B200FLOW_ENOCONV) return rc;
+  BF_TRY(download(ctx, x, (const double *)d_x, 2 * N));
+  API_SYNC(ctx);
+  return rc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // evaluation / export edges
 // ------------------------------------------------------------------------------------------------

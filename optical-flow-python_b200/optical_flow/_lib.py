@@ -88,6 +88,8 @@ _SIGS = {
                                    _vp, _vp, _vp, _vp],
     "b200flow_solve_increment_mc": [C.POINTER(Params), C.c_double, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                     _vp, _ip, _dp],
+    "b200flow_solve_rhs_mc": [C.POINTER(Params), C.c_double, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp,
+                              _vp, _ip, _dp],
     "b200flow_detect_occlusion_mc": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp],
     "b200flow_flow_error": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "b200flow_flow_error_dev": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],

@@ -98,8 +98,42 @@ class FlowOperator:
             self._b = self._each(None)[1].reshape(-1, order='F')
         return self._b
 
-    def solve(self, owner):
-        """A x = b on the device; x as (H, W, 2)."""
+    def tocsc(self):
+        """The operator as a scipy.sparse CSC matrix (what the reference's flow_operator returns), recovered from the
+        matrix-free device operator by probing: the 2N x 2N matrix couples (u, v) of a pixel with itself and its four
+        neighbours, so 3 x 3 pixel colourings x 2 components = 18 products A @ e give every entry exactly."""
+        from scipy import sparse
+        H, W = self.hw
+        N = H * W
+        yy, xx = np.mgrid[0:H, 0:W]
+        colour = (yy % 3) * 3 + (xx % 3)
+        rows, cols, vals = [], [], []
+        pix = np.arange(N).reshape(H, W, order='F')              # column-major pixel index of the reference's vectorisation
+        for comp in range(2):
+            for c in range(9):
+                e = np.zeros((H, W, 2))
+                e[:, :, comp][colour == c] = 1.0
+                y = self.matvec(e.reshape(-1, order='F')).reshape((H, W, 2), order='F')
+                # a response at pixel q (component k) comes from the unique probe pixel of colour c within distance 1 of q
+                for k in range(2):
+                    for dy, dx in ((0, 0), (0, 1), (0, -1), (1, 0), (-1, 0)):
+                        if (dy or dx) and k != comp:
+                            continue                                 # the two components couple only inside a pixel
+                        src = np.zeros((H, W), dtype=bool)
+                        src[colour == c] = True
+                        qy, qx = yy + dy, xx + dx                    # q = p + d for every probe pixel p
+                        ok = src & (qy >= 0) & (qy < H) & (qx >= 0) & (qx < W)
+                        v = y[qy[ok], qx[ok], k]
+                        nz = v != 0.0
+                        rows.append((k * N + pix[qy[ok], qx[ok]])[nz])
+                        cols.append((comp * N + pix[yy[ok], xx[ok]])[nz])
+                        vals.append(v[nz])
+        return sparse.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=self.shape)
+
+    tocsr = lambda self: self.tocsc().tocsr()      # noqa: E731
+
+    def solve(self, owner, rhs=None):
+        """A x = b on the device (b = the assembled right-hand side, or the caller's rhs); x as (H, W, 2)."""
         H, W = self.hw
         if len(self.terms) == 1 and abs(self.terms[0][0] - 1.0) < 1e-15:
             P, alpha = self.terms[0][1]._c_params(single=True), 0.0
@@ -112,9 +146,16 @@ class FlowOperator:
         x = np.empty((H, W, 2))
         iters = _lib.C.c_int(0)
         rel = _lib.C.c_double(0.0)
-        _lib.default_context().call("b200flow_solve_increment_mc", P, float(alpha), _lib.ptr(self._uv),
-                                    _lib.ptr(self._duv), _lib.ptr(self._It), _lib.ptr(self._Ix), _lib.ptr(self._Iy), H, W,
-                                    self.nc, _lib.ptr(x), _lib.C.byref(iters), _lib.C.byref(rel), allow_noconv=True)
+        if rhs is None:
+            _lib.default_context().call("b200flow_solve_increment_mc", P, float(alpha), _lib.ptr(self._uv),
+                                        _lib.ptr(self._duv), _lib.ptr(self._It), _lib.ptr(self._Ix), _lib.ptr(self._Iy), H, W,
+                                        self.nc, _lib.ptr(x), _lib.C.byref(iters), _lib.C.byref(rel), allow_noconv=True)
+        else:
+            r = _lib.f64(np.asarray(rhs, dtype=float).reshape((H, W, 2), order='F'))
+            _lib.default_context().call("b200flow_solve_rhs_mc", P, float(alpha), _lib.ptr(self._uv),
+                                        _lib.ptr(self._duv), _lib.ptr(self._It), _lib.ptr(self._Ix), _lib.ptr(self._Iy), H, W,
+                                        self.nc, _lib.ptr(r), _lib.ptr(x), _lib.C.byref(iters), _lib.C.byref(rel),
+                                        allow_noconv=True)
         owner.last_stats = {"pcg_iters": iters.value, "relres": rel.value}
         return x
 
@@ -297,9 +338,8 @@ class BaseOpticalFlow(ABC):
         if not isinstance(A, FlowOperator):
             raise TypeError("_solve_linear_system needs the FlowOperator returned by flow_operator (no sparse matrices "
                             "are built on this path)")
-        if b is not None and not (b is A.b or np.array_equal(np.asarray(b).reshape(-1), A.b)):
-            raise NotImplementedError("custom right-hand sides are not supported; pass the b returned by flow_operator")
-        return A.solve(self).reshape(uv_shape)
+        custom = b is not None and not (b is A.b or np.array_equal(np.asarray(b).reshape(-1), A.b))
+        return A.solve(self, rhs=b if custom else None).reshape(uv_shape)
 
     def _build_pyramid(self, images, levels, spacing):
         smooth_sigma = np.sqrt(spacing) / np.sqrt(2)

@@ -232,3 +232,26 @@ def test_sor_e2e(preset, params):
     g = load_golden("sor.npz")
     uv = estimate_flow(g["rgb1"].astype(float), g["rgb2"].astype(float), preset, params)
     assert_close(uv, g["e2e_" + preset], 1e-3, "solver='sor' estimate_flow(%s)" % preset)
+
+
+def test_operator_as_sparse_matrix_and_custom_rhs(systems):
+    """API edges of the reference's flow_operator / _solve_linear_system (base.py:87-114): the operator as a scipy.sparse
+    matrix (FlowOperator.tocsc, recovered exactly by 18 probing products) and a solve with the caller's own right-hand side."""
+    from scipy import sparse
+    from optical_flow import load_of_method
+    ope = load_of_method("classic+nl")
+    uv = systems["uv"]
+    It, Ix, Iy = systems["cnl_It"], systems["cnl_Ix"], systems["cnl_Iy"]
+    A, b, _, _ = ope.flow_operator(uv, np.zeros_like(uv), It, Ix, Iy)
+    M = A.tocsc()
+    assert sparse.issparse(M) and M.shape == A.shape
+    assert abs(M - M.T).max() <= 1e-12 * abs(M).max(), "symmetric"
+    assert M.nnz <= 6 * A.shape[0]
+    probe = _f(systems["probe"])
+    assert _rel(M @ probe, _f(systems["cnl_a0_Ap"])) < 1e-11
+    assert _rel(M.diagonal(), _f(systems["cnl_a0_diag"])) < 1e-12
+    rng = np.random.default_rng(11)
+    rhs = rng.standard_normal(b.shape)
+    x = ope._solve_linear_system(A, rhs, uv.shape)
+    true_rel = float(np.linalg.norm(rhs - M @ _f(x)) / np.linalg.norm(rhs))
+    assert true_rel <= 1e-10, true_rel
