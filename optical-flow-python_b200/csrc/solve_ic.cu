@@ -371,25 +371,27 @@ __device__ __forceinline__ void band_barrier_reduce(const BandParams &bp, unsign
     }
     va = warp_sum(va);
     vb = warp_sum(vb);
+    // the exchange with the peers runs on one lane per rank: lane r publishes to rank r and then waits for rank r's flag
+    // (world <= 8 <= 32), so its latency is that of ONE NVLink round trip, not of `world` of them
+    const bool act = lane < bp.world;
+    if (act) {
+      st_sys_f64(&bp.peer[lane]->xs[slot][bp.rank][0], va);
+      st_sys_f64(&bp.peer[lane]->xs[slot][bp.rank][1], vb);
+    }
+    __threadfence_system();                         // ONE release fence: the band's vectors and the sums, before the flags
+    if (act) {
+      st_relaxed_sys_u64(&bp.peer[lane]->flag[bp.rank], seq);
+      while (ld_relaxed_sys_u64(&self->flag[lane]) < seq && ++spins < limit) {}
+    }
+    __threadfence_system();                         // ONE acquire fence after all the flags have been seen
+    const bool timed_out = __any_sync(0xffffffffu, spins >= limit);
     if (lane == 0) {
-#ifdef BAND_DEBUG
-      printf("[band] rank %d barrier %llu: local arrive done after %lld spins (G %d), sums %.6e %.6e\n", bp.rank, seq, spins, (int)gridDim.x, va, vb);
-#endif
-      for (int r = 0; r < bp.world; ++r) {
-        st_sys_f64(&bp.peer[r]->xs[slot][bp.rank][0], va);
-        st_sys_f64(&bp.peer[r]->xs[slot][bp.rank][1], vb);
-      }
-      __threadfence_system();                       // ONE release fence: the band's vectors and the sums, before the flags
-      for (int r = 0; r < bp.world; ++r) st_relaxed_sys_u64(&bp.peer[r]->flag[bp.rank], seq);
-      for (int r = 0; r < bp.world; ++r)
-        while (ld_relaxed_sys_u64(&self->flag[r]) < seq && ++spins < limit) {}
-      __threadfence_system();                       // ONE acquire fence after all the flags have been seen
       double sa = 0.0, sb = 0.0;
       for (int r = 0; r < bp.world; ++r) { sa += ld_sys_f64(&self->xs[slot][r][0]); sb += ld_sys_f64(&self->xs[slot][r][1]); }
 #ifdef BAND_DEBUG
-      printf("[band] rank %d barrier %llu: peers arrived after %lld spins, global %.6e %.6e\n", bp.rank, seq, spins, sa, sb);
+      printf("[band] rank %d barrier %llu: global %.6e %.6e\n", bp.rank, seq, sa, sb);
 #endif
-      if (spins >= limit) {                         // timed out (now or earlier): poison the sums, the solve ends as failed
+      if (timed_out) {                              // timed out (now or earlier): poison the sums, the solve ends as failed
         if (limit > 0) self->error = seq;
         sa = sb = __longlong_as_double(0x7ff8000000000000LL);
       }
