@@ -73,12 +73,27 @@ def estimate_flow_batch(ims1, ims2, method='classic+nl-fast', params=None, devic
     if ope.pyramid_levels < 1:
         P.pyramid_levels, P.auto_level = 0, 1
     ope._apply_solver(P)
-    st = _lib.Stats()
     ctx = _lib.default_context(device)
     uv = ctx.pinned_empty((B, H, W, 2))       # page-locked: the result comes back in one DMA
-    ctx.call("b200flow_estimate_rgb8", P, B, H, W, _lib.ptr(ims1), _lib.ptr(ims2), int(ope.color_images is not None),
-             _lib.ptr(uv), _lib.C.byref(st))
-    return (uv, st.as_dict()) if return_stats else uv
+    use_color = int(ope.color_images is not None)
+    MAXB = 128                                # systems one persistent solve tracks (one scalar-update thread per system)
+    stats = None
+    for b0 in range(0, B, MAXB):
+        b1 = min(B, b0 + MAXB)
+        st = _lib.Stats()
+        ctx.call("b200flow_estimate_rgb8", P, b1 - b0, H, W, _lib.ptr(ims1[b0:b1]), _lib.ptr(ims2[b0:b1]), use_color,
+                 _lib.ptr(uv[b0:b1]), _lib.C.byref(st))
+        d = st.as_dict()
+        if stats is None:
+            stats = d
+        else:                                   # larger batches run as chunks of 128 pairs: counters and times add up
+            for k in ("pcg_iters", "pcg_pixel_iters", "kernel_launches", "not_converged", "solver_ms", "warp_ms", "filter_ms",
+                      "pre_ms", "total_ms", "solves"):
+                stats[k] += d[k]
+            for name, kd in d["kernels"].items():
+                for k in kd:
+                    stats["kernels"][name][k] += kd[k]
+    return (uv, stats) if return_stats else uv
 
 
 def shard_indices(n_items, rank, world_size):
