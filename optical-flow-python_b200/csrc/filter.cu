@@ -319,17 +319,18 @@ __device__ __forceinline__ unsigned wm_pack(double w, double scale) {
 // Stage 3 keeps bisecting on that one-sample-per-lane set (a step is now ~25 instructions) down to <= 8 survivors and
 //   finishes exactly: every survivor evaluates S at its own value (S(L) + an all-pairs pass over the survivors) and
 //   the smallest one with S >= half is the answer.  The result is always one of the window's samples.
-template <int NPL>
+template <int NPL, int NFULL>
 __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const double (&w)[NPL],
                                                   const unsigned (&pk)[NPL], int n, double half, double2 *scratch,
                                                   int lane) {
   // value range in fp32 with outward rounding (FMNMX instead of fp64 compare + select pairs)
+  // (slots k < NFULL hold a real sample in every lane: no +inf padding to filter out of the maximum there)
   float flo = __double2float_rd(x[0]), fhi = -INFINITY;
 #pragma unroll
   for (int k = 0; k < NPL; ++k) {
     flo = fminf(flo, __double2float_rd(x[k]));
     const float u = __double2float_ru(x[k]);
-    fhi = fmaxf(fhi, u == INFINITY ? -INFINITY : u);
+    fhi = fmaxf(fhi, (k >= NFULL && u == INFINITY) ? -INFINITY : u);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -345,7 +346,8 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
     if (!snap) {
       unsigned acc = 0u;
 #pragma unroll
-      for (int k = 0; k < NPL; ++k) acc += x[k] <= p ? pk[k] : 0u;
+      for (int k = 0; k < NPL; ++k)
+        if (x[k] <= p) acc += pk[k];                       // DSETP + predicated IADD (a select would cost a third instruction)
       acc = __reduce_add_sync(0xffffffffu, acc);
       const int c = (int)(acc & 511u);
       const unsigned f = acc >> 9;
@@ -435,7 +437,9 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
 #ifndef WM_MINB
 #define WM_MINB 3                // CTAs per SM the register budget is cut for: 3 (80 registers) 106 ms of filter time per bench step, 2 (128) 116 ms, 4 (64) 126 ms
 #endif
-template <int NPL>
+// NFULL = number of slots k that hold a real sample in every lane (n / 32, or 0 for the generic instantiation): those slots
+// need no padding logic at all -- for the 15 x 15 window of the presets that is 7 of the 8 slots.
+template <int NPL, int NFULL>
 __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const double2 *__restrict__ cand,
                                                                   const double2 *__restrict__ base,
                                                                   const double *__restrict__ color, int C,
@@ -492,7 +496,8 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
       cd += d2 * d2;
       const double wk = exp_nonpos(-cd * inv2s2) * cq.w;
       // np.maximum(w, 1e-10); padding slots get weight 0
-      w[k] = ((vmask >> k) & 1u) ? (wk > 1e-10 ? wk : 1e-10) : 0.0;
+      const double wfl = wk > 1e-10 ? wk : 1e-10;
+      w[k] = (k < NFULL || ((vmask >> k) & 1u)) ? wfl : 0.0;
       tot += w[k];
     }
 #pragma unroll
@@ -502,15 +507,15 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
     {
       const double scale = 4194304.0 / tot;                  // 2^22 / total
 #pragma unroll
-      for (int k = 0; k < NPL; ++k) pk[k] = ((vmask >> k) & 1u) ? wm_pack(w[k], scale) : 0u;
+      for (int k = 0; k < NPL; ++k) pk[k] = (k < NFULL || ((vmask >> k) & 1u)) ? wm_pack(w[k], scale) : 0u;
     }
     // padding slots: x = +inf with zero weight (never counted, weighed or bracketed)
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) x[k] = ((vmask >> k) & 1u) ? s_uv[org + qoff[k]].x : INFINITY;
-    const double mu = weighted_select<NPL>(x, w, pk, n, half, s_scr, lane);
+    for (int k = 0; k < NPL; ++k) x[k] = (k < NFULL || ((vmask >> k) & 1u)) ? s_uv[org + qoff[k]].x : INFINITY;
+    const double mu = weighted_select<NPL, NFULL>(x, w, pk, n, half, s_scr, lane);
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) x[k] = ((vmask >> k) & 1u) ? s_uv[org + qoff[k]].y : INFINITY;
-    const double mv = weighted_select<NPL>(x, w, pk, n, half, s_scr, lane);
+    for (int k = 0; k < NPL; ++k) x[k] = (k < NFULL || ((vmask >> k) & 1u)) ? s_uv[org + qoff[k]].y : INFINITY;
+    const double mv = weighted_select<NPL, NFULL>(x, w, pk, n, half, s_scr, lane);
     if (lane == 0) {
       long long gi = off + (long long)py * W + px;
       if (base) {
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
   }
 }
 
-template <int NPL>
+template <int NPL, int NFULL>
 static int launch_wmedian(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color, int C,
                           const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
   int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
@@ -536,16 +541,16 @@ static int launch_wmedian(b200flow_ctx *ctx, const double2 *cand, const double2 
     static size_t smem_set[64] = {0};
     std::lock_guard<std::mutex> lock(mu);
     if (smem_set[ctx->device & 63] < smem) {
-      BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL, NFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       // same shared-memory configuration as the persistent solver (solve_ic.cu IC_CARVEOUT_PCT): with concurrent
       // sub-batches CTAs of both kernels share an SM, which they only can under one L1 / shared-memory split
-      BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL>, cudaFuncAttributePreferredSharedMemoryCarveout, 64));
+      BF_CUDA(ctx, cudaFuncSetAttribute(wmedian_kernel<NPL, NFULL>, cudaFuncAttributePreferredSharedMemoryCarveout, 64));
       smem_set[ctx->device & 63] = smem;
     }
   }
   dim3 grd((unsigned)cdiv(W, WM_TW), (unsigned)cdiv(H, WM_TH), B);
   double inv2s2 = 1.0 / (2.0 * (sigma_i * sigma_i));
-  BF_LAUNCH(ctx, (wmedian_kernel<NPL>), grd, WM_WARPS * 32, smem, cand, base, color, C, occ, H, W, hsz, inv2s2, out);
+  BF_LAUNCH(ctx, (wmedian_kernel<NPL, NFULL>), grd, WM_WARPS * 32, smem, cand, base, color, C, occ, H, W, hsz, inv2s2, out);
   return 0;
 }
 
@@ -554,11 +559,12 @@ int k_weighted_median(b200flow_ctx *ctx, const double2 *cand, const double2 *bas
   if (hsz < 0) return set_err(ctx, B200FLOW_EINVAL, "area_hsz must be >= 0");
   if (C < 1 || C > 3) return set_err(ctx, B200FLOW_EINVAL, "weighted median supports 1..3 colour channels, got %d", C);
   int n = (2 * hsz + 1) * (2 * hsz + 1);
-  if (n <= 32) return launch_wmedian<1>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
-  if (n <= 64) return launch_wmedian<2>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
-  if (n <= 128) return launch_wmedian<4>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
-  if (n <= 256) return launch_wmedian<8>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
-  if (n <= 512) return launch_wmedian<16>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n <= 32) return launch_wmedian<1, 0>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n <= 64) return launch_wmedian<2, 0>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n <= 128) return launch_wmedian<4, 0>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n == 225) return launch_wmedian<8, 7>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);   // the presets' 15 x 15 window
+  if (n <= 256) return launch_wmedian<8, 0>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
+  if (n <= 512) return launch_wmedian<16, 0>(ctx, cand, base, color, C, occ, B, H, W, hsz, sigma_i, out);
   return set_err(ctx, B200FLOW_EINVAL, "area_hsz=%d (window %d samples) unsupported (max 10)", hsz, n);
 }
 
