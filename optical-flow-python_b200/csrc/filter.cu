@@ -409,12 +409,19 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
   }
   // stage 3b: S at every survivor from an all-pairs pass over the survivors, in fixed point; a survivor whose S is too
   // close to half to call (true value in [f, f + count]) gets the exact fp64 sum over the whole window instead
+  // (the survivors go back to the scratch row, packed, and every lane reads them all: one broadcast shared load per pair
+  // instead of three shuffles + a bit scan)
   unsigned acc = 0u;
-  for (unsigned m = __ballot_sync(0xffffffffu, valid); m; m &= m - 1) {
-    const int j = __ffs(m) - 1;
-    const double xj = __shfl_sync(0xffffffffu, me.x, j);
-    const unsigned pj = __shfl_sync(0xffffffffu, mypk, j);
-    if (xj <= me.x) acc += pj;
+  {
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    const int nv = __popc(vm);
+    if (valid) scratch[__popc(vm & lt)] = make_double2(me.x, __hiloint2double(0, (int)mypk));
+    __syncwarp();
+    for (int j = 0; j < nv; ++j) {
+      const double2 e = scratch[j];
+      if (e.x <= me.x) acc += (unsigned)__double2loint(e.y);
+    }
+    __syncwarp();
   }
   const unsigned fi = FL + (acc >> 9), ci = (unsigned)nL + (acc & 511u);
   bool ge = fi >= WM_HALF_FIX + 4u;
