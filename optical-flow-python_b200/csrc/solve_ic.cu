@@ -545,13 +545,16 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
 
   // ---- strip ownership: the strips of the unfinished systems, in compact order, are dealt to the CTAs in
   //      contiguous chunks of s_tpc; recomputed (identically by every CTA) whenever a system finishes
-#define REMAP()                                                                         \
+#define REMAP() MAP_WHERE(s_state[b] != 1)
+  // the same dealing restricted to the systems that satisfy `cond` (the reliable update deals the systems it replaces the
+  // residual of over the WHOLE grid, see below)
+#define MAP_WHERE(cond)                                                                 \
   {                                                                                     \
     __syncthreads();                                                                    \
     if (tid == 0) {                                                                     \
       int n = 0;                                                                        \
       for (int b = 0; b < B; ++b) {                                                     \
-        if (s_state[b] != 1) { s_act[n] = b; s_pos[b] = n; ++n; } else s_pos[b] = -1;   \
+        if (cond) { s_act[n] = b; s_pos[b] = n; ++n; } else s_pos[b] = -1;              \
       }                                                                                 \
       s_nact = n;                                                                       \
       long long tt = (long long)n * tps;                                                \
@@ -863,23 +866,31 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
     }
     if (__syncthreads_or(rel)) {
       // ---------------- reliable update: r = b - A (x + y + alpha p) in fp64, then z = M^-1 r ----------------
-      for (int a = a_first; a <= a_last; ++a) {
-        TILE_RANGE(a)
-        if (s_state[b] != 3) continue;
-        const double alpha = s_alpha[b];
-        double acc_rz = 0.0, acc_rr = 0.0, acc_dummy = 0.0;
-        for (long long v = ta; v < tb; ++v) {
-          int px, py; long long i; bool ok;
-          PIXEL_OF(v, px, py, i, ok)
-          if (!ok) continue;
-          const double2 rt = ic_true_residual<BAND>(P, bp, i, px, py, pnew, alpha);
-          r[i] = make_float2((float)rt.x, (float)rt.y);
-          acc_rr += rt.x * rt.x + rt.y * rt.y;
+      // Only a few systems replace their residual in a given iteration, and every CTA waits at the barrier that follows:
+      // with the regular dealing the 1/B of the CTAs that own such a system did ~1.5 iterations' worth of work while all
+      // the others idled (ncu stall samples: that barrier alone was 10 % of the kernel).  For the update the strips of
+      // exactly those systems are therefore RE-DEALT over the whole grid, and the regular dealing is restored afterwards
+      // (every CTA derives both from the same shared state, so nothing has to be communicated).
+      MAP_WHERE(s_state[b] == 3)
+      {
+        OWN_RANGE()
+        for (int a = a_first; a <= a_last; ++a) {
+          TILE_RANGE(a)
+          const double alpha = s_alpha[b];
+          double acc_rz = 0.0, acc_rr = 0.0, acc_dummy = 0.0;
+          for (long long v = ta; v < tb; ++v) {
+            int px, py; long long i; bool ok;
+            PIXEL_OF(v, px, py, i, ok)
+            if (!ok) continue;
+            const double2 rt = ic_true_residual<BAND>(P, bp, i, px, py, pnew, alpha);
+            r[i] = make_float2((float)rt.x, (float)rt.y);
+            acc_rr += rt.x * rt.x + rt.y * rt.y;
+          }
+          __syncthreads();                       // r of the own strips is complete (same ownership in both passes)
+          for (long long t = ta + ty; t < tb; t += IC_NSTRIP) PHASE_B_TILE(t, 0.f, false, acc_rz, acc_dummy)
+          ic_block_sum2(acc_rz, acc_rr, sm_red);
+          if (tid == 0) { part_d[(long long)b * G + cta] = acc_rz; part_e[(long long)b * G + cta] = acc_rr; }
         }
-        __syncthreads();                       // r of the own strips is complete (same ownership in both passes)
-        for (long long t = ta + ty; t < tb; t += IC_NSTRIP) PHASE_B_TILE(t, 0.f, false, acc_rz, acc_dummy)
-        ic_block_sum2(acc_rz, acc_rr, sm_red);
-        if (tid == 0) { part_d[(long long)b * G + cta] = acc_rz; part_e[(long long)b * G + cta] = acc_rr; }
       }
       SYNC_REDUCE(part_d, part_e, 3)
       int fin = 0;
@@ -917,7 +928,9 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
           s_rz[b] = rz;
         }
       }
-      if (__syncthreads_or(fin)) {
+      const int any_fin = __syncthreads_or(fin);
+      REMAP()                                  // back to the regular dealing (same systems as at the top of the iteration)
+      if (any_fin) {
         // systems that just finished: fold the pending y + alpha p into x (own pixels only), then re-deal the tiles
         for (int a = a_first; a <= a_last; ++a) {
           TILE_RANGE(a)
@@ -947,6 +960,7 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
 #endif
 #undef IC_TICK
 #undef REMAP
+#undef MAP_WHERE
 #undef C_LO
 #undef C_HI
 #undef OWN_RANGE
