@@ -929,26 +929,32 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
         }
       }
       const int any_fin = __syncthreads_or(fin);
-      REMAP()                                  // back to the regular dealing (same systems as at the top of the iteration)
       if (any_fin) {
-        // systems that just finished: fold the pending y + alpha p into x (own pixels only), then re-deal the tiles
-        for (int a = a_first; a <= a_last; ++a) {
-          TILE_RANGE(a)
-          if (s_state[b] != 2) continue;
-          const double alpha = s_alpha[b];
-          for (long long v = ta; v < tb; ++v) {
-            int px, py; long long i; bool ok;
-            PIXEL_OF(v, px, py, i, ok)
-            if (!ok) continue;
-            double2 xc = x[i];
-            float2 yc = y[i], pc = pnew[i];
-            x[i] = make_double2(xc.x + ((double)yc.x + alpha * (double)pc.x), xc.y + ((double)yc.y + alpha * (double)pc.y));
+        // systems that just finished: fold the pending y + alpha p into x -- their pixels dealt over the whole grid like
+        // the update above (a pass over one system by the few CTAs that own it would show up as skew at the next
+        // barrier) -- then re-deal the strips of the systems that are left
+        MAP_WHERE(s_state[b] == 2)
+        {
+          OWN_RANGE()
+          for (int a = a_first; a <= a_last; ++a) {
+            TILE_RANGE(a)
+            const double alpha = s_alpha[b];
+            for (long long v = ta; v < tb; ++v) {
+              int px, py; long long i; bool ok;
+              PIXEL_OF(v, px, py, i, ok)
+              if (!ok) continue;
+              double2 xc = x[i];
+              float2 yc = y[i], pc = pnew[i];
+              x[i] = make_double2(xc.x + ((double)yc.x + alpha * (double)pc.x), xc.y + ((double)yc.y + alpha * (double)pc.y));
+            }
           }
         }
         __syncthreads();
         if (tid < B && s_state[tid] == 2) s_state[tid] = 1;
         REMAP()
         n_active = s_nact;
+      } else {
+        REMAP()                                // back to the regular dealing (same systems as at the top of the iteration)
       }
     }
     { float2 *t = pold; pold = pnew; pnew = t; }
