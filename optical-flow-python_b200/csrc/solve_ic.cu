@@ -287,7 +287,10 @@ struct BandSync {                        // at offset 0 of every rank's arena bl
   unsigned long long seq;                // barriers this rank has completed (written by its CTA 0 only; persists across kernels)
   unsigned long long release;            // local release: this rank's CTAs may leave barrier `release`
   unsigned long long flag[B200FLOW_MAX_BAND_RANKS];     // flag[r]: last barrier rank r has arrived at (written by rank r, remotely)
-  double xs[2][B200FLOW_MAX_BAND_RANKS][2];             // xs[parity][r]: rank r's local sums of that barrier (written by rank r)
+  double xs[2][B200FLOW_MAX_BAND_RANKS][2];             // (unused since the sums travel with their sequence number, below)
+  // ll[parity][r][i] = {rank r's i-th local sum, the barrier's sequence number}: ONE 16-byte store each, so the value and the
+  // flag that validates it arrive together and no fence has to order them (the "LL" scheme of collective libraries)
+  unsigned long long ll[2][B200FLOW_MAX_BAND_RANKS][2][2];
   double gs[2][2];                       // the global sums of that barrier (written by the local CTA 0)
   unsigned long long error;              // != 0: a spin loop timed out (a peer died); the result is invalid
 };
@@ -302,6 +305,15 @@ struct BandParams {
 __device__ __forceinline__ void st_sys_f64(double *p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys_ll(unsigned long long *p, double v, unsigned long long seq) {
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+}
+__device__ __forceinline__ bool ld_sys_ll(const unsigned long long *p, unsigned long long seq, double &v) {
+  unsigned long long a, b;
+  asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)a);
+  return b >= seq;
 }
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -373,21 +385,27 @@ __device__ __forceinline__ void band_barrier_reduce(const BandParams &bp, unsign
     vb = warp_sum(vb);
     // the exchange with the peers runs on one lane per rank: lane r publishes to rank r and then waits for rank r's flag
     // (world <= 8 <= 32), so its latency is that of ONE NVLink round trip, not of `world` of them
+    // Ordering without system-scope fences (each costs microseconds): (i) the band's vectors were written to THIS GPU's
+    // L2 before the CTAs arrived (their gpu-scope fences) and the neighbours read them there, over NVLink, with loads that
+    // bypass their own L1; (ii) each sum travels in one 16-byte store together with the sequence number that validates it.
     const bool act = lane < bp.world;
+    double ra = 0.0, rb = 0.0;
     if (act) {
-      st_sys_f64(&bp.peer[lane]->xs[slot][bp.rank][0], va);
-      st_sys_f64(&bp.peer[lane]->xs[slot][bp.rank][1], vb);
+      st_sys_ll(&bp.peer[lane]->ll[slot][bp.rank][0][0], va, seq);
+      st_sys_ll(&bp.peer[lane]->ll[slot][bp.rank][1][0], vb, seq);
+      bool oka = false, okb = false;
+      while (!(oka && okb) && ++spins < limit) {
+        oka = ld_sys_ll(&self->ll[slot][lane][0][0], seq, ra);
+        okb = ld_sys_ll(&self->ll[slot][lane][1][0], seq, rb);
+      }
     }
-    __threadfence_system();                         // ONE release fence: the band's vectors and the sums, before the flags
-    if (act) {
-      st_relaxed_sys_u64(&bp.peer[lane]->flag[bp.rank], seq);
-      while (ld_relaxed_sys_u64(&self->flag[lane]) < seq && ++spins < limit) {}
-    }
-    __threadfence_system();                         // ONE acquire fence after all the flags have been seen
     const bool timed_out = __any_sync(0xffffffffu, spins >= limit);
+    double sa = 0.0, sb = 0.0;
+    for (int r = 0; r < bp.world; ++r) {            // rank order: the same bits on every rank
+      sa += __shfl_sync(0xffffffffu, ra, r);
+      sb += __shfl_sync(0xffffffffu, rb, r);
+    }
     if (lane == 0) {
-      double sa = 0.0, sb = 0.0;
-      for (int r = 0; r < bp.world; ++r) { sa += ld_sys_f64(&self->xs[slot][r][0]); sb += ld_sys_f64(&self->xs[slot][r][1]); }
 #ifdef BAND_DEBUG
       printf("[band] rank %d barrier %llu: global %.6e %.6e\n", bp.rank, seq, sa, sb);
 #endif
@@ -576,12 +594,17 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
   const long long ta = tbase > t0 ? tbase : t0;                                                  \
   const long long tb = tbase + tps < t1 ? tbase + tps : t1;                                      \
   const long long base = (long long)b * HW;
+  // strip number -> strip coordinates.  One GPU: row-major.  Band mode: COLUMN-major, so that the strips of the band's first
+  // and last row -- whose phase A waits for a remote load of the neighbour's halo row, ~3 us each -- are spread over all CTAs
+  // instead of sitting back to back in the first and the last few (a CTA's chunk of consecutive strips is then a vertical run)
+#define STRIP_X(tl) (BAND ? (tl) / P.tiles_y : (tl) % P.tiles_x)
+#define STRIP_Y(tl) (BAND ? (tl) % P.tiles_y : (tl) / P.tiles_x)
   // pixel of this thread in strip v of the current system (phase A: one pixel per thread, the strip is the 32 x 8 thread tile)
 #define PIXEL_OF(v, px, py, i, ok)                                                               \
   {                                                                                              \
     const int tl = (int)((v) - tbase);                                                           \
-    px = (tl % P.tiles_x) * 32 + tx;                                                             \
-    py = Y0 + (tl / P.tiles_x) * 8 + ty;                                                         \
+    px = STRIP_X(tl) * 32 + tx;                                                                  \
+    py = Y0 + STRIP_Y(tl) * 8 + ty;                                                              \
     ok = (v) < tb && px < W && py < Y1;                                                          \
     i = ok ? base + (long long)py * W + px : base;                                               \
   }
@@ -628,8 +651,8 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
 #define PHASE_B_TILE(t, alpha_f, use_ap, acc_rz, acc_rr)                                                       \
   {                                                                                                            \
     const int tl = (int)((t) - tbase);                                                                         \
-    const int px = (tl % P.tiles_x) * 32 + tx;                                                                 \
-    const int py0 = Y0 + (tl / P.tiles_x) * 8;                                                                 \
+    const int px = STRIP_X(tl) * 32 + tx;                                                                      \
+    const int py0 = Y0 + STRIP_Y(tl) * 8;                                                                      \
     const long long i0 = base + (long long)py0 * W + px;                                                       \
     const int sl0 = ic_slot(ty * 8, tx);                                                                       \
     float2 rc[8], ac[8];                                                                                       \
@@ -681,8 +704,8 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
       double acc_rz = 0.0, acc_bb = 0.0;
       for (long long t = ta + ty; t < tb; t += IC_NSTRIP) {     // strips of this CTA, dealt round-robin to its warps
         const int tl = (int)(t - tbase);
-        const int px = (tl % P.tiles_x) * 32 + tx;
-        const int py0 = Y0 + (tl / P.tiles_x) * 8;
+        const int px = STRIP_X(tl) * 32 + tx;
+        const int py0 = Y0 + STRIP_Y(tl) * 8;
 #pragma unroll 2
         for (int u = 0; u < 8; ++u) {
           const int py = py0 + u;
@@ -974,6 +997,8 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
 #undef SYNC_REDUCE
 #undef TILE_RANGE
 #undef PIXEL_OF
+#undef STRIP_X
+#undef STRIP_Y
 #undef PHASE_B_TILE
 }
 
