@@ -597,8 +597,13 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
   // strip number -> strip coordinates.  One GPU: row-major.  Band mode: COLUMN-major, so that the strips of the band's first
   // and last row -- whose phase A waits for a remote load of the neighbour's halo row, ~3 us each -- are spread over all CTAs
   // instead of sitting back to back in the first and the last few (a CTA's chunk of consecutive strips is then a vertical run)
+#ifdef IC_COLMAJOR      // tuning: column-major on one GPU too
+#define STRIP_X(tl) ((tl) / P.tiles_y)
+#define STRIP_Y(tl) ((tl) % P.tiles_y)
+#else
 #define STRIP_X(tl) (BAND ? (tl) / P.tiles_y : (tl) % P.tiles_x)
 #define STRIP_Y(tl) (BAND ? (tl) % P.tiles_y : (tl) / P.tiles_x)
+#endif
   // pixel of this thread in strip v of the current system (phase A: one pixel per thread, the strip is the 32 x 8 thread tile)
 #define PIXEL_OF(v, px, py, i, ok)                                                               \
   {                                                                                              \
