@@ -172,3 +172,21 @@ def test_weighted_median_tie_fuzz():
         np.testing.assert_array_equal(got[same], ref[same], err_msg="case %d" % i)
         if i == 0:
             np.testing.assert_array_equal(got, ref, err_msg="exact-arithmetic case")
+
+
+@pytest.mark.parametrize("shape", [(40, 300), (300, 40), (257, 129)])
+def test_spline_prefilter_segments_vs_oracle(shape):
+    """Cubic-spline partial_deriv on lines longer than one prefilter segment (128 samples + 64 of warm-up, warp.cu): rows,
+    columns and both, against the oracle's whole-line recursion (scipy semantics)."""
+    import flow_oracle as fo
+    from optical_flow.utils.derivatives import partial_deriv
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    images = np.round(rng.random((H, W, 2)) * 255)
+    yy, xx = np.mgrid[0:H, 0:W].astype(float)
+    uv = np.stack([1.3 * np.sin(xx / 17.0) + 0.4, 0.9 * np.cos(yy / 13.0) - 0.2], axis=2)
+    h = np.array([1, -8, 0, 8, -1]) / 12.0
+    got = partial_deriv(images, uv, "cubic", h, 0.5)
+    want = fo.partial_deriv(images, uv, "cubic", h, 0.5)
+    for g, w, name in zip(got, want, ("It", "Ix", "Iy")):
+        assert_close(g, w, 1e-9, "segmented prefilter %dx%d %s" % (H, W, name))
