@@ -717,6 +717,17 @@ def main():
             gbs = gb_i / (ms_i / 1e3) if ms_i > 0 else 0.0
             stages[name] = {"ms_per_step": ms_i, "launch_groups_per_step": k_calls[i] / args.steps, "algorithmic_GB_per_step": gb_i,
                             "GBps": gbs, "frac_of_hbm_peak": gbs / peak, "bound": "issue" if name == "weighted_median" else "hbm"}
+        # issue-slot utilisation of the compute-bound weighted median: from the committed ncu --set full capture of this build
+        try:
+            for ln in open(os.path.join(ROOT, "profiles", "r02_ncu_full_kernels.jsonl")):
+                rec = json.loads(ln) if ln.startswith("{") else {}
+                if "wmedian" in str(rec.get("kernel")) and "weighted_median" in stages:
+                    stages["weighted_median"].update({"issue_slot_pct_ncu": rec.get("issue_active_pct"),
+                                                      "fp64_pipe_pct_ncu": rec.get("fp64_pipe_pct"),
+                                                      "warp_instructions_per_pixel_ncu": rec.get("warp_instr", 0) / float(16 * H * W),
+                                                      "ncu_source": "profiles/r02_ncu_full_kernels.jsonl (one launch, B = 16, 640x480)"})
+        except (OSError, ValueError):
+            pass
         line["stages"] = stages
         if world == 1 and not args.no_variants:
             line["variants"] = run_variants(args, ctx, d1, d2, duv, B, local_rank, peak)
