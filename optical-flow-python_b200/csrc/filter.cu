@@ -346,8 +346,9 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
     if (!snap) {
       unsigned acc = 0u;
 #pragma unroll
-      for (int k = 0; k < NPL; ++k)
-        if (x[k] <= p) acc += pk[k];                       // DSETP + predicated IADD (a select would cost a third instruction)
+      for (int k = 0; k < NPL; ++k)                      // DSETP + predicated IADD, spelled out: the compiler's own choice is
+        asm("{\n\t.reg .pred q;\n\tsetp.le.f64 q, %1, %2;\n\t@q add.u32 %0, %0, %3;\n\t}"      // SEL + 3-input adds + predicate
+            : "+r"(acc) : "d"(x[k]), "d"(p), "r"(pk[k]));                                    // spills: 28 instead of 17 per step
       acc = __reduce_add_sync(0xffffffffu, acc);
       const int c = (int)(acc & 511u);
       const unsigned f = acc >> 9;
