@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
       cd += d2 * d2;
       const double wk = exp_nonpos(-cd * inv2s2) * cq.w;
       // np.maximum(w, 1e-10); padding slots get weight 0
-      const double wfl = wk > 1e-10 ? wk : 1e-10;
+      const double wfl = fmax(wk, 1e-10);
       w[k] = (k < NFULL || ((vmask >> k) & 1u)) ? wfl : 0.0;
       tot += w[k];
     }
