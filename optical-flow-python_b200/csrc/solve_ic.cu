@@ -501,15 +501,51 @@ __device__ __forceinline__ void ic_grid_barrier(unsigned *counter, unsigned &tar
 #endif
 
 
-template <bool BAND>
-__device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams &bp) {
+// Cluster mode (small levels): ONE THREAD-BLOCK CLUSTER PER SYSTEM.  A level of 30 x 40 ... 120 x 160 pixels is latency bound:
+// its iteration is two grid barriers (atomic counter + polling over up to 296 CTAs, ~6 us each) around a few microseconds of
+// work, and all systems of the batch wait for each other.  Here a system's strips are dealt over the CTAs of one cluster, the
+// two barriers of an iteration are the hardware cluster barrier (barrier.cluster), and the clusters never synchronise with
+// each other: a system that has converged simply ends.  The vectors stay where they are (global memory: a small level lives
+// in L2); the body below is the same code with B = 1 and every pointer moved to the cluster's system.
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+  // the gpu-scope fences on both sides do for the data what they do in ic_grid_barrier: publish this CTA's rows, and drop the
+  // SM's L1 before rows written by the other CTAs of the cluster are read
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x == 0) __threadfence();
+  __syncthreads();
+}
+
+enum { IC_MODE_GRID = 0, IC_MODE_BAND = 1, IC_MODE_CLUSTER = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void pcg_ic_body(const MixParams &Pin, const BandParams &bp) {
+  constexpr bool BAND = MODE == IC_MODE_BAND, CLUS = MODE == IC_MODE_CLUSTER;
 #ifdef IC_CG_BARRIER
   cg::grid_group grid = cg::this_grid();
 #endif
+  const int Btot = Pin.sys.B;                      // systems of the launch (cluster mode: one of them per cluster)
+  const int G = CLUS ? (int)cluster_nctarank() : (int)gridDim.x, cta = CLUS ? (int)cluster_ctarank() : (int)blockIdx.x;
+  const int sysid = CLUS ? (int)blockIdx.x / G : 0;
+  MixParams Pc;                                    // cluster mode: the parameter block of this cluster's system
+  if (CLUS) {
+    Pc = Pin;
+    const long long o = (long long)sysid * Pin.sys.H * Pin.sys.W;
+    Pc.sys.B = 1;
+    Pc.sys.D += o; Pc.sys.a12 += o; Pc.sys.WH += o; Pc.sys.WV += o; Pc.sys.rhs += o;
+    Pc.x += o;
+    Pc.m.r += o; Pc.m.z += o; Pc.m.p += o; Pc.m.p2 += o; Pc.m.Ap += o; Pc.m.y += o;
+    Pc.m.D += o; Pc.m.WH += o; Pc.m.WV += o; Pc.m.a12 += o;
+    Pc.w.ic_c0 += o; Pc.w.ic_cw += o;
+    Pc.w.partial += (long long)sysid * 5 * G;      // five slices of G partials for this system
+  }
+  const MixParams &P = CLUS ? Pc : Pin;
   const LinSys &S = P.sys;
   const int Y0 = BAND ? bp.y0 : 0;                 // first pixel row of this rank's band
   const int Y1 = BAND ? bp.y1 : S.H;               // one past its last row
-  const int G = gridDim.x, cta = blockIdx.x;
   const int H = S.H, W = S.W, B = S.B;
   const long long HW = (long long)H * W;
   const long long n_all = (long long)B * HW;
@@ -551,15 +587,15 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
   float2 *Df = P.m.D, *WHf = P.m.WH, *WVf = P.m.WV;
   float *a12f = P.m.a12;
   double2 *x = P.x;
-  int *done_g = P.w.flags + 1;
+  int *done_g = P.w.flags + 1 + sysid;
 #ifndef IC_CG_BARRIER
   unsigned *bar_counter = reinterpret_cast<unsigned *>(P.w.flags);   // flags[0]: zeroed before every launch
   unsigned bar_target = 0u;
 #endif
   unsigned long long band_seq = 0ull;
   if (BAND) band_seq = *(volatile unsigned long long *)&bp.self->seq;   // this rank's barrier count so far (own writes only)
-  int *iters_g = P.w.flags + 1 + B;
-  double *relres_g = P.w.scal;
+  int *iters_g = P.w.flags + 1 + Btot + sysid;
+  double *relres_g = P.w.scal + sysid;
 
   // ---- strip ownership: the strips of the unfinished systems, in compact order, are dealt to the CTAs in
   //      contiguous chunks of s_tpc; recomputed (identically by every CTA) whenever a system finishes
@@ -619,7 +655,10 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
 #define SYNC_REDUCE(pa, pb, want) { IC_GRID_SYNC(); REDUCE_ALL(pa, pb, want) }
 #else
 #define SYNC_REDUCE(pa, pb, want)                                                               \
-  if (BAND) {                                                                                   \
+  if (CLUS) {                                                                                   \
+    cluster_barrier();                                                                          \
+    REDUCE_ALL(pa, pb, want)                                                                    \
+  } else if (BAND) {                                                                            \
     double ga_, gb_;                                                                            \
     band_barrier_reduce(bp, bar_counter, bar_target, band_seq, (pa), (pb), C_LO(0), C_HI(0), ga_, gb_);   \
     if (tid == 0) { s_ta[0] = ga_; s_tb[0] = gb_; }                                             \
@@ -1009,12 +1048,17 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &P, const BandParams
 
 __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_kernel(MixParams P) {
   BandParams none;
-  pcg_ic_body<false>(P, none);
+  pcg_ic_body<IC_MODE_GRID>(P, none);
 }
 
 #ifndef IC_CG_BARRIER
+__global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_cluster_kernel(MixParams P) {
+  BandParams none;
+  pcg_ic_body<IC_MODE_CLUSTER>(P, none);
+}
+
 __global__ void __launch_bounds__(IC_THREADS, 512 / IC_THREADS) pcg_ic_band_kernel(MixParams P, BandParams bp) {
-  pcg_ic_body<true>(P, bp);
+  pcg_ic_body<IC_MODE_BAND>(P, bp);
 }
 #endif
 
@@ -1057,6 +1101,39 @@ int pcg_ic_grid(b200flow_ctx *ctx, int *grid_out) {
   return 0;
 }
 
+#ifndef IC_CG_BARRIER
+// small levels: one cluster of `cs` CTAs per system (pcg_ic_body<IC_MODE_CLUSTER>); 0 = not available
+static int ic_cluster_size(b200flow_ctx *ctx) {
+  static std::mutex mu;
+  static int cs_of[64] = {0};
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lock(mu);
+  const int d = ctx->device & 63;
+  if (!done[d]) {
+    done[d] = true;
+    int want = 16;
+    if (const char *e = getenv("B200FLOW_CLUSTER_SIZE")) want = atoi(e);
+    if (want >= 2 && cudaFuncSetAttribute(pcg_ic_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IC_SMEM) == cudaSuccess &&
+        cudaFuncSetAttribute(pcg_ic_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, IC_CARVEOUT_PCT) == cudaSuccess) {
+      if (want > 8) cudaFuncSetAttribute(pcg_ic_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      for (int cs = want; cs >= 2; cs >>= 1) {           // the largest cluster the device schedules with this footprint
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(IC_THREADS); cfg.dynamicSmemBytes = IC_SMEM;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = cs; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, pcg_ic_cluster_kernel, &cfg) == cudaSuccess && n >= 1) { cs_of[d] = cs; break; }
+      }
+    }
+    cudaGetLastError();
+  }
+  return cs_of[d];
+}
+#endif
+
 int k_pcg_ic_launch(b200flow_ctx *ctx, MixParams P, int grid_max) {
   const LinSys &sys = P.sys;
   if (sys.B > MAXB)
@@ -1064,6 +1141,31 @@ int k_pcg_ic_launch(b200flow_ctx *ctx, MixParams P, int grid_max) {
   P.tiles_x = (int)cdiv(sys.W, 32);      // strips of 8 rows x 32 columns: the unit that is dealt to the CTAs
   P.tiles_y = (int)cdiv(sys.H, 8);
   P.tiles_per_sys = P.tiles_x * P.tiles_y;
+#ifndef IC_CG_BARRIER
+  {
+    // OFF by default (B200FLOW_CLUSTER_MAXPIX=24000 switches it on for levels up to 120 x 160).  Measured on B200, 16 systems,
+    // us per iteration, grid barrier / clusters of 8 / 16 CTAs: 30x40 10.2 / 9.8 / 18.8, 60x80 12.1 / 12.2 / 20.9, 120x160
+    // 16.6 / 22.7 / 29.8 (only eight 16-CTA clusters of this footprint are resident at a time: two waves).  The ~9 us floor
+    // of a tiny iteration is the chain of dependent global-memory round trips inside the two phases, not the barrier.
+    long long maxpix = 0;
+    if (const char *e = getenv("B200FLOW_CLUSTER_MAXPIX")) maxpix = atoll(e);
+    const int cs = (long long)sys.H * sys.W <= maxpix ? ic_cluster_size(ctx) : 0;
+    if (cs >= 2 && (long long)sys.B * 5 * cs <= (long long)5 * sys.B * grid_max) {
+      P.debug = 0;
+      P.w.grid = cs;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3((unsigned)(sys.B * cs)); cfg.blockDim = dim3(IC_THREADS); cfg.dynamicSmemBytes = IC_SMEM;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = cs; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      BF_CUDA(ctx, cudaLaunchKernelEx(&cfg, pcg_ic_cluster_kernel, P));
+      return 0;
+    }
+  }
+#endif
   const long long total = (long long)P.tiles_per_sys * sys.B;
   int G = grid_max;
   if ((long long)G > total) G = (int)total;
