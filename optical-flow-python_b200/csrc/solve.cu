@@ -546,9 +546,9 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
           zc[u] = z[ii]; po[u] = pold[ii];
           zl[u] = z[jl]; pl[u] = pold[jl]; zr[u] = z[jr]; pr[u] = pold[jr];
           zu[u] = z[ju]; pu[u] = pold[ju]; zd[u] = z[jd]; pd[u] = pold[jd];
-          sd[u] = __ldg(&Df[ii]); swr[u] = __ldg(&WHf[ii]); swd[u] = __ldg(&WVf[ii]);
-          swl[u] = __ldg(&WHf[jl]); swu[u] = __ldg(&WVf[ju]);
-          sa12[u] = __ldg(&a12f[ii]);
+          sd[u] = Df[ii]; swr[u] = WHf[ii]; swd[u] = WVf[ii];
+          swl[u] = WHf[jl]; swu[u] = WVf[ju];
+          sa12[u] = a12f[ii];
           yc[u] = y[ii];
         }
 #pragma unroll
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(PCG_THREADS, MIX_MINB) pcg_mixed_kernel(MixPar
           int px, py;
           PIXEL_OF(t + u, px, py, i[u], ok[u])
           rc[u] = r[i[u]]; ac[u] = Ap[i[u]];
-          m11[u] = __ldg(&Minv[i[u]]); m12[u] = __ldg(&Minv[n_all + i[u]]); m22[u] = __ldg(&Minv[2 * n_all + i[u]]);
+          m11[u] = Minv[i[u]]; m12[u] = Minv[n_all + i[u]]; m22[u] = Minv[2 * n_all + i[u]];
         }
 #pragma unroll
         for (int u = 0; u < MIX_UB; ++u) {

@@ -854,13 +854,13 @@ __device__ __forceinline__ void pcg_ic_body(const MixParams &Pin, const BandPara
           if (BAND && py[u] + 1 == Y1 && bp.dn_delta != 0) {
             zd[u] = ld_sys_f2(band_shift(z + jd, bp.dn_delta)); pd[u] = ld_sys_f2(band_shift(pold + jd, bp.dn_delta));
           } else { zd[u] = z[jd]; pd[u] = pold[jd]; }
-          sd[u] = __ldg(&Df[ii]); swr[u] = __ldg(&WHf[ii]); swd[u] = __ldg(&WVf[ii]);
-          swl[u] = __ldg(&WHf[jl]);
+          sd[u] = Df[ii]; swr[u] = WHf[ii]; swd[u] = WVf[ii];
+          swl[u] = WHf[jl];
           if (BAND && py[u] == Y0) {                              // the fp32 copy only covers the band: take the fp64 edge
             const double2 e = __ldg(&S.WV[ju]);
             swu[u] = make_float2((float)e.x, (float)e.y);
-          } else swu[u] = __ldg(&WVf[ju]);
-          sa12[u] = __ldg(&a12f[ii]);
+          } else swu[u] = WVf[ju];
+          sa12[u] = a12f[ii];
           yc[u] = y[ii];
         }
 #pragma unroll
