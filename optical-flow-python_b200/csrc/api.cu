@@ -77,6 +77,7 @@ void b200flow_ctx_destroy(b200flow_ctx *ctx) {
     if (c->solver_stream) cudaStreamDestroy(c->solver_stream);
     if (c->ev_s0) cudaEventDestroy(c->ev_s0);
     if (c->ev_s1) cudaEventDestroy(c->ev_s1);
+    if (c->powtab) cudaFree(c->powtab);
     delete c;
   }
   band_release(ctx);
@@ -84,6 +85,7 @@ void b200flow_ctx_destroy(b200flow_ctx *ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaStreamSynchronize(ctx->stream);
   for (auto &c : ctx->chunks) cudaFree(c.base);
+  if (ctx->powtab) cudaFree(ctx->powtab);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -40,6 +40,10 @@ struct b200flow_ctx {
   // resident grid sizes of the persistent solver kernels on this device (filled once by solve.cu; 0 = not yet queried)
   int grid_pcg = 0, grid_mixed = 0, grid_ic = 0;
   int ic_ctas_per_sm = 0;           // occupancy of pcg_ic_kernel as reported by the runtime
+  // table behind the generalized Charbonnier weight y^(a-1) of the assembly kernels (warp.cu, pow_table_kernel):
+  // built on this context's stream whenever the exponent changes
+  double *powtab = nullptr;
+  double powtab_a = 0.0;
   // Concurrent sub-batches (pipeline.cu, run_pipeline_split): a batch of B pairs is cut into `nsplit` groups that run the
   // whole coarse-to-fine loop on their own stream and arena, so that the bandwidth-bound solver of one group overlaps the
   // issue-bound weighted median of another.  The persistent solver then takes solver_ctas_per_sm CTAs per SM (so that the

@@ -16,6 +16,12 @@ struct PenaltySet {            // everything the assemble kernel needs to form t
   double lambda, lambda_q, alpha;
   int hs;                      // 1: Horn-Schunck form (unit weights * lambda/sigmaS2, d = 1/sigmaD2)
   double hs_w, hs_d;
+  // generalized Charbonnier weights through a table (warp.cu, pow_tab): filled by the assembly launchers, never by callers
+  const double *ptab = nullptr;  // device table built for exponent ptab_a - 1; null = exp/log path
+  double ptab_a = 0.0;
+  double pc[6] = {0, 0, 0, 0, 0, 0};   // binomial coefficients C(a-1, 1..6)
+  int fast = 0;                  // Classic+NL-shaped set: edge weight = eq + er y^(a-1), data weight = dq + dr y^(a-1)
+  double eq = 0, er = 0, s2s = 0, dq = 0, dr = 0, s2d = 0;
 };
 
 struct LinSys {                // matrix-free 2N x 2N system, B systems of H x W pixels

@@ -27,13 +27,91 @@ __device__ __forceinline__ double pen_weight(const b200flow_penalty &pn, double 
 }
 
 // Same weights for the ASSEMBLY kernels.  The generalized Charbonnier weight 2a (s2 + x^2)^(a-1) is the only penalty that
-// needs a transcendental (nine of them per pixel in Classic+NL / classic++): pow() costs ~200 instructions (double-double
-// logarithm behind a call), exp((a-1) log y) ~70 inlined ones.  Relative error <= |(a-1) ln y| 2^-53 + 2 ulp < 2e-15
-// for y in [1e-12, 1e12] -- the operator tests hold the assembled A, b to 1e-11 relative, and the public
-// RobustFunction.deriv_over_x (pen_eval below) keeps pow().
-__device__ __forceinline__ double pen_weight_asm(const b200flow_penalty &pn, double x) {
-  if (pn.kind == 3) return 2.0 * pn.p1 * exp((pn.p1 - 1.0) * log(pn.p0 * pn.p0 + x * x));
+// needs a transcendental (nine of them per pixel in Classic+NL / classic++).  pow() costs ~200 fp64 instructions,
+// exp((a-1) log y) ~200 too once both are inlined (62 % of warp_assemble_kernel's instructions, ncu source page, round 2),
+// and B200 issues fp64 at half rate -- the kernel was bound by that pipe, not by HBM.  pow_tab() splits
+//     y = 2^e m,  m = (1 + d) / inv_k     (k = the top 7 mantissa bits, inv_k = 1 / bin centre, |d| <= 2^-8)
+//     y^c = 2^(c e) * (1/inv_k)^c * (1 + d)^c
+// with the first two factors read from a 3 KB table built once per exponent (pow_table_kernel) and the third a degree-6
+// binomial series (truncation < 1e-17): 9 fp64 instructions, relative error <= 4 ulp.  Outside 2^-64 <= y < 2^64 (and for
+// exponents the table was not built for) the exp/log form remains.  The operator tests hold the assembled A, b to 1e-11
+// relative; the public RobustFunction.deriv_over_x (pen_eval below) keeps pow().
+constexpr int POWTAB_BINS = 128, POWTAB_EXP = 128, POWTAB_DOUBLES = 2 * POWTAB_BINS + POWTAB_EXP;
+
+__global__ void pow_table_kernel(double *tab, double c) {
+  const int k = threadIdx.x;
+  if (k < POWTAB_BINS) {
+    const double inv = 1.0 / (1.0 + (k + 0.5) / POWTAB_BINS);
+    tab[2 * k] = inv;
+    tab[2 * k + 1] = pow(1.0 / inv, c);
+  }
+  if (k < POWTAB_EXP) tab[2 * POWTAB_BINS + k] = exp2(c * (double)(k - POWTAB_EXP / 2));
+}
+
+__device__ __forceinline__ double pow_tab(const PenaltySet &ps, double y, double c) {
+  const long long bits = __double_as_longlong(y);
+  const int e = (int)(bits >> 52) - 1023 + POWTAB_EXP / 2;
+  if ((unsigned)e >= (unsigned)POWTAB_EXP) return exp(c * log(y));   // also inf / nan / subnormal
+  const int k = (int)(bits >> 45) & (POWTAB_BINS - 1);
+  const double m = __longlong_as_double((bits & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
+  const double2 t = __ldg(reinterpret_cast<const double2 *>(ps.ptab) + k);
+  const double sc = t.y * __ldg(ps.ptab + 2 * POWTAB_BINS + e);
+  const double d = fma(m, t.x, -1.0);
+  double p = fma(ps.pc[5], d, ps.pc[4]);
+  p = fma(p, d, ps.pc[3]);
+  p = fma(p, d, ps.pc[2]);
+  p = fma(p, d, ps.pc[1]);
+  p = fma(p, d, ps.pc[0]);
+  return fma(p * d, sc, sc);
+}
+
+__device__ __forceinline__ double pen_weight_asm(const PenaltySet &ps, const b200flow_penalty &pn, double x) {
+  if (pn.kind == 3) {
+    const double y = pn.p0 * pn.p0 + x * x;
+    if (ps.ptab && pn.p1 == ps.ptab_a) return 2.0 * pn.p1 * pow_tab(ps, y, pn.p1 - 1.0);
+    return 2.0 * pn.p1 * exp((pn.p1 - 1.0) * log(y));
+  }
   return pen_weight(pn, x);
+}
+
+// Host side of pow_tab(): pick the exponent the table serves (the first generalized Charbonnier penalty of the set; the
+// reference's methods use one `a` throughout), rebuild the table on the context's stream when it changed.
+static int attach_pow_table(b200flow_ctx *ctx, PenaltySet *ps) {
+  ps->ptab = nullptr;
+  ps->fast = 0;
+  if (ps->hs || !(ps->alpha < 1.0)) return 0;
+  const b200flow_penalty *cand[5] = {&ps->rho_d, &ps->rho_su[0], &ps->rho_su[1], &ps->rho_sv[0], &ps->rho_sv[1]};
+  const b200flow_penalty *pn = nullptr;
+  for (auto q : cand)
+    if (q->kind == 3) { pn = q; break; }
+  if (!pn || getenv("B200FLOW_POW_EXPLOG")) return 0;
+  if (!ctx->powtab) BF_CUDA(ctx, cudaMalloc(&ctx->powtab, POWTAB_DOUBLES * sizeof(double)));
+  if (ctx->powtab_a != pn->p1) {
+    BF_LAUNCH(ctx, pow_table_kernel, 1, POWTAB_BINS, 0, ctx->powtab, pn->p1 - 1.0);
+    ctx->powtab_a = pn->p1;
+  }
+  ps->ptab = ctx->powtab;
+  ps->ptab_a = pn->p1;
+  double c = pn->p1 - 1.0, b = 1.0;
+  for (int k = 1; k <= 6; ++k) { b = b * (c - (k - 1)) / k; ps->pc[k - 1] = b; }
+  // the Classic+NL shape of the set: one generalized Charbonnier for the four spatial terms and one for the data term (same
+  // exponent), quadratic partners -> the two-constant form of blended_edge<true> / blended_data<true>
+  auto same = [](const b200flow_penalty &a, const b200flow_penalty &b) { return a.kind == b.kind && a.p0 == b.p0 && a.p1 == b.p1; };
+  const b200flow_penalty &rs = ps->rho_su[0], &qs = ps->qua_su[0];
+  bool fast = rs.kind == 3 && rs.p1 == pn->p1 && ps->rho_d.kind == 3 && ps->rho_d.p1 == pn->p1 && qs.kind == 0 && ps->qua_d.kind == 0;
+  for (int k = 0; k < 2; ++k)
+    fast = fast && same(ps->rho_su[k], rs) && same(ps->rho_sv[k], rs) && same(ps->qua_su[k], qs) && same(ps->qua_sv[k], qs);
+  ps->fast = fast && !getenv("B200FLOW_ASM_GENERIC");
+  if (ps->fast) {
+    const double a = pn->p1, al = ps->alpha;
+    ps->eq = al > 0.0 ? al * (ps->lambda_q * (2.0 / (qs.p0 * qs.p0))) : 0.0;
+    ps->er = (1.0 - al) * (ps->lambda * (2.0 * a));
+    ps->s2s = rs.p0 * rs.p0;
+    ps->dq = al > 0.0 ? al * (2.0 / (ps->qua_d.p0 * ps->qua_d.p0)) : 0.0;
+    ps->dr = (1.0 - al) * (2.0 * a);
+    ps->s2d = ps->rho_d.p0 * ps->rho_d.p0;
+  }
+  return 0;
 }
 
 __device__ double pen_eval(const b200flow_penalty &pn, int d_type, double x, double tdist_const) {
@@ -400,20 +478,34 @@ __device__ __forceinline__ Deriv pixel_deriv(const double *__restrict__ im1, con
 // ------------------------------------------------------------------------------------------------
 // IRLS weights + system assembly for one pixel (flow_operator + GNC blend)
 // ------------------------------------------------------------------------------------------------
+// FAST: the penalty set is the Classic+NL family's -- one generalized Charbonnier penalty for all four spatial terms, one (same
+// exponent) for the data term, quadratic GNC partners (attach_pow_table checks it) -- so the per-call dispatch on the penalty kind
+// and its constant loads (two thirds of the kernel's instructions once pow became a table) fold into two host-side constants per
+// term: w = eq + er * y^(a-1).
+template <bool FAST>
 __device__ __forceinline__ double blended_edge(const PenaltySet &ps, const b200flow_penalty &rob,
                                                const b200flow_penalty &qua, double delta) {
+  if (FAST) {
+    if (ps.er == 0.0) return ps.eq;
+    return fma(ps.er, pow_tab(ps, fma(delta, delta, ps.s2s), ps.ptab_a - 1.0), ps.eq);
+  }
   if (ps.hs) return ps.hs_w;
   double w = 0.0;
-  if (ps.alpha > 0.0) w = w + ps.alpha * (ps.lambda_q * pen_weight_asm(qua, delta));
-  if (ps.alpha < 1.0) w = w + (1.0 - ps.alpha) * (ps.lambda * pen_weight_asm(rob, delta));
+  if (ps.alpha > 0.0) w = w + ps.alpha * (ps.lambda_q * pen_weight_asm(ps, qua, delta));
+  if (ps.alpha < 1.0) w = w + (1.0 - ps.alpha) * (ps.lambda * pen_weight_asm(ps, rob, delta));
   return w;
 }
 
+template <bool FAST>
 __device__ __forceinline__ double blended_data(const PenaltySet &ps, double it_lin) {
+  if (FAST) {
+    if (ps.dr == 0.0) return ps.dq;
+    return fma(ps.dr, pow_tab(ps, fma(it_lin, it_lin, ps.s2d), ps.ptab_a - 1.0), ps.dq);
+  }
   if (ps.hs) return ps.hs_d;
   double d = 0.0;
-  if (ps.alpha > 0.0) d = d + ps.alpha * pen_weight_asm(ps.qua_d, it_lin);
-  if (ps.alpha < 1.0) d = d + (1.0 - ps.alpha) * pen_weight_asm(ps.rho_d, it_lin);
+  if (ps.alpha > 0.0) d = d + ps.alpha * pen_weight_asm(ps, ps.qua_d, it_lin);
+  if (ps.alpha < 1.0) d = d + (1.0 - ps.alpha) * pen_weight_asm(ps, ps.rho_d, it_lin);
   return d;
 }
 
@@ -421,9 +513,10 @@ __device__ __forceinline__ double blended_data(const PenaltySet &ps, double it_l
 struct DataTerm { double a11, a22, a12, bu, bv; };
 
 // single-channel frames (flow_operator's `else` branch, classic_nl.py:344-351)
+template <bool FAST>
 __device__ __forceinline__ DataTerm data_term_single(const PenaltySet &ps, Deriv dv, double2 dc) {
   double it_lin = dv.It + dv.Ix * dc.x + dv.Iy * dc.y;
-  double d = blended_data(ps, it_lin);
+  double d = blended_data<FAST>(ps, it_lin);
   DataTerm t;
   t.a11 = d * dv.Ix * dv.Ix; t.a22 = d * dv.Iy * dv.Iy; t.a12 = d * dv.Ix * dv.Iy;
   t.bu = d * it_lin * dv.Ix; t.bv = d * it_lin * dv.Iy;
@@ -436,7 +529,7 @@ struct DataAccum {
   double sd = 0.0, ix2 = 0.0, iy2 = 0.0, ixy = 0.0, itx = 0.0, ity = 0.0;
   __device__ __forceinline__ void add(const PenaltySet &ps, Deriv dv, double2 dc) {
     double it_lin = dv.It + dv.Ix * dc.x + dv.Iy * dc.y;
-    sd += blended_data(ps, it_lin);
+    sd += blended_data<false>(ps, it_lin);
     ix2 += dv.Ix * dv.Ix; iy2 += dv.Iy * dv.Iy; ixy += dv.Ix * dv.Iy;
     itx += it_lin * dv.Ix; ity += it_lin * dv.Iy;
   }
@@ -454,11 +547,11 @@ struct DataAccum {
 // only the tile's first column / row recompute their left / up edge (the weight is an even function of the flow
 // difference, so both sides get the same bits).  8 -> 4.3 penalty evaluations per pixel.  Must be called by every thread
 // of the CTA (`in` = the thread has a pixel); SHARE = false is the plain per-pixel form for callers without a tile.
-template <bool SHARE>
+template <bool SHARE, bool FAST>
 __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const double2 *__restrict__ uv,
                                                const double2 *__restrict__ duv, int H, int W, int x, int y, bool in,
                                                DataTerm dt, const LinSys &sys, long long gi, double2 (*sH)[32],
-                                               double2 (*sV)[32]) {
+                                               double2 (*sV)[32], double2 *sL) {
   const long long i = (long long)y * W + x;
   double2 c0 = make_double2(0.0, 0.0), c = c0;
   double whu = 0.0, whv = 0.0, wvu = 0.0, wvv = 0.0;        // own right / down edges (stored)
@@ -475,15 +568,15 @@ __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const doubl
     c = make_double2(c0.x + dc.x, c0.y + dc.y);             // uv + duv (for the weights)
     if (x + 1 < W) {   // right: delta = f[x+1] - f[x]
       nb(i + 1, n0, n);
-      whu = blended_edge(ps, ps.rho_su[0], ps.qua_su[0], n.x - c.x);
-      whv = blended_edge(ps, ps.rho_sv[0], ps.qua_sv[0], n.y - c.y);
+      whu = blended_edge<FAST>(ps, ps.rho_su[0], ps.qua_su[0], n.x - c.x);
+      whv = blended_edge<FAST>(ps, ps.rho_sv[0], ps.qua_sv[0], n.y - c.y);
       lr_u = whu * (c0.x - n0.x);
       lr_v = whv * (c0.y - n0.y);
     }
     if (y + 1 < H) {   // down
       nb(i + W, n0, n);
-      wvu = blended_edge(ps, ps.rho_su[1], ps.qua_su[1], n.x - c.x);
-      wvv = blended_edge(ps, ps.rho_sv[1], ps.qua_sv[1], n.y - c.y);
+      wvu = blended_edge<FAST>(ps, ps.rho_su[1], ps.qua_su[1], n.x - c.x);
+      wvv = blended_edge<FAST>(ps, ps.rho_sv[1], ps.qua_sv[1], n.y - c.y);
       ld_u = wvu * (c0.x - n0.x);
       ld_v = wvv * (c0.y - n0.y);
     }
@@ -491,6 +584,19 @@ __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const doubl
   if (SHARE) {
     sH[threadIdx.y][threadIdx.x] = make_double2(whu, whv);
     sV[threadIdx.y][threadIdx.x] = make_double2(wvu, wvv);
+    // the left edges of the tile's first column belong to the CTA next door: eight lanes of ONE warp recompute them (lane 0 of
+    // every warp doing its own would run the evaluation eight times per CTA at 1/32 utilisation)
+    if (threadIdx.y == 1 && threadIdx.x < 8) {
+      const int xl = x - (int)threadIdx.x, yl = y - 1 + (int)threadIdx.x;     // pixel (tile x0, tile y0 + lane)
+      if (xl > 0 && xl < W && yl < H) {
+        const long long il = (long long)yl * W + xl;
+        double2 a0, a, b0, b;
+        nb(il, a0, a);
+        nb(il - 1, b0, b);
+        sL[threadIdx.x] = make_double2(blended_edge<FAST>(ps, ps.rho_su[0], ps.qua_su[0], a.x - b.x),
+                                       blended_edge<FAST>(ps, ps.rho_sv[0], ps.qua_sv[0], a.y - b.y));
+      }
+    }
     __syncthreads();
   }
   if (!in) return;
@@ -499,10 +605,10 @@ __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const doubl
   if (x > 0) {       // left edge belongs to pixel x-1: delta = f[x] - f[x-1]
     nb(i - 1, n0, n);
     double wu, wv;
-    if (SHARE && threadIdx.x > 0) { const double2 e = sH[threadIdx.y][threadIdx.x - 1]; wu = e.x; wv = e.y; }
+    if (SHARE) { const double2 e = threadIdx.x > 0 ? sH[threadIdx.y][threadIdx.x - 1] : sL[threadIdx.y]; wu = e.x; wv = e.y; }
     else {
-      wu = blended_edge(ps, ps.rho_su[0], ps.qua_su[0], c.x - n.x);
-      wv = blended_edge(ps, ps.rho_sv[0], ps.qua_sv[0], c.y - n.y);
+      wu = blended_edge<FAST>(ps, ps.rho_su[0], ps.qua_su[0], c.x - n.x);
+      wv = blended_edge<FAST>(ps, ps.rho_sv[0], ps.qua_sv[0], c.y - n.y);
     }
     lu += wu * (c0.x - n0.x);
     lv += wv * (c0.y - n0.y);
@@ -513,8 +619,8 @@ __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const doubl
     double wu, wv;
     if (SHARE && threadIdx.y > 0) { const double2 e = sV[threadIdx.y - 1][threadIdx.x]; wu = e.x; wv = e.y; }
     else {
-      wu = blended_edge(ps, ps.rho_su[1], ps.qua_su[1], c.x - n.x);
-      wv = blended_edge(ps, ps.rho_sv[1], ps.qua_sv[1], c.y - n.y);
+      wu = blended_edge<FAST>(ps, ps.rho_su[1], ps.qua_su[1], c.x - n.x);
+      wv = blended_edge<FAST>(ps, ps.rho_sv[1], ps.qua_sv[1], c.y - n.y);
     }
     lu += wu * (c0.x - n0.x);
     lv += wv * (c0.y - n0.y);
@@ -528,14 +634,14 @@ __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const doubl
 
 // algorithmic bytes per pixel, single-channel frames: read uv 16 + im1,I1x,I1y 24 + gathered source 32,
 // write D 16 + a12 8 + WH 16 + WV 16 + rhs 16  = 144 B   (NC channels: 88 + 56 NC)
-template <bool MULTI>   // MULTI: NC > 1 (kept out of the single-channel instantiation: it doubles the register count)
+template <bool MULTI, bool FAST>   // MULTI: NC > 1 (kept out of the single-channel instantiation: it doubles the register count)
 __global__ void __launch_bounds__(256, MULTI ? 1 : 3) warp_assemble_kernel(const double *__restrict__ frames, long long bstride, int NC,
                                      const double *__restrict__ I1x,
                                      const double *__restrict__ I1y, const double4 *__restrict__ src2,
                                      const double2 *__restrict__ uv, const double2 *__restrict__ duv, int H, int W,
                                      int interp, double blend, PenaltySet ps, LinSys sys, double *__restrict__ It,
                                      double *__restrict__ Ix, double *__restrict__ Iy, int do_assemble) {
-  __shared__ double2 sH[8][32], sV[8][32];                 // the tile's right / down edge weights (assemble_pixel)
+  __shared__ double2 sH[8][32], sV[8][32], sL[8];          // the tile's right / down edge weights (assemble_pixel)
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
   const bool in = x < W && y < H;
@@ -551,7 +657,7 @@ __global__ void __launch_bounds__(256, MULTI ? 1 : 3) warp_assemble_kernel(const
       Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride, I1x + off, I1y + off, src2 + off, H, W, x, y, f,
                              interp, blend);
       if (It) { It[off + i] = dv.It; Ix[off + i] = dv.Ix; Iy[off + i] = dv.Iy; }
-      dt = data_term_single(ps, dv, dc);
+      dt = data_term_single<FAST>(ps, dv, dc);
     } else {
       DataAccum acc;
       for (int c = 0; c < NC; ++c) {
@@ -565,14 +671,15 @@ __global__ void __launch_bounds__(256, MULTI ? 1 : 3) warp_assemble_kernel(const
     }
   }
   if (do_assemble)
-    assemble_pixel<true>(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, in, dt, sys, off + i, sH, sV);
+    assemble_pixel<true, FAST>(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, in, dt, sys, off + i, sH, sV, sL);
 }
 
 // It, Ix, Iy: [B][NC][H][W]
+template <bool FAST>
 __global__ void __launch_bounds__(256, 3) assemble_from_deriv_kernel(const double *__restrict__ It, const double *__restrict__ Ix,
                                            const double *__restrict__ Iy, int NC, const double2 *__restrict__ uv,
                                            const double2 *__restrict__ duv, int H, int W, PenaltySet ps, LinSys sys) {
-  __shared__ double2 sH[8][32], sV[8][32];
+  __shared__ double2 sH[8][32], sV[8][32], sL[8];
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y * blockDim.y + threadIdx.y;
   const bool in = x < W && y < H;
@@ -585,7 +692,7 @@ __global__ void __launch_bounds__(256, 3) assemble_from_deriv_kernel(const doubl
     if (NC == 1) {
       Deriv dv;
       dv.It = It[off + i]; dv.Ix = Ix[off + i]; dv.Iy = Iy[off + i];
-      dt = data_term_single(ps, dv, dc);
+      dt = data_term_single<FAST>(ps, dv, dc);
     } else {
       DataAccum acc;
       for (int c = 0; c < NC; ++c) {
@@ -597,28 +704,38 @@ __global__ void __launch_bounds__(256, 3) assemble_from_deriv_kernel(const doubl
       dt = acc.finish(NC);
     }
   }
-  assemble_pixel<true>(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, in, dt, sys, off + i, sH, sV);
+  assemble_pixel<true, FAST>(ps, uv + off, duv ? duv + off : nullptr, H, W, x, y, in, dt, sys, off + i, sH, sV, sL);
 }
 
 int k_warp_assemble(b200flow_ctx *ctx, const double *frames, long long bstride, int NC, const double *I1x, const double *I1y,
                     const double4 *src2, const double2 *uv, const double2 *duv, int B, int H, int W, int interp, double blend,
-                    const PenaltySet &ps, LinSys sys, double *It, double *Ix, double *Iy) {
+                    const PenaltySet &ps_in, LinSys sys, double *It, double *Ix, double *Iy) {
   if (interp < 0 || interp > 2) return set_err(ctx, B200FLOW_EINVAL, "Unknown interpolation method: %d", interp);
+  PenaltySet ps = ps_in;
+  if (sys.D != nullptr) BF_TRY(attach_pow_table(ctx, &ps));
   dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
   int do_assemble = sys.D != nullptr;
-  if (NC == 1)
-    BF_LAUNCH(ctx, warp_assemble_kernel<false>, grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp,
+  if (NC == 1 && ps.fast)
+    BF_LAUNCH(ctx, (warp_assemble_kernel<false, true>), grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp,
+              blend, ps, sys, It, Ix, Iy, do_assemble);
+  else if (NC == 1)
+    BF_LAUNCH(ctx, (warp_assemble_kernel<false, false>), grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp,
               blend, ps, sys, It, Ix, Iy, do_assemble);
   else
-    BF_LAUNCH(ctx, warp_assemble_kernel<true>, grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp,
+    BF_LAUNCH(ctx, (warp_assemble_kernel<true, false>), grd, blk, 0, frames, bstride, NC, I1x, I1y, src2, uv, duv, H, W, interp,
               blend, ps, sys, It, Ix, Iy, do_assemble);
   return 0;
 }
 
 int k_assemble_from_deriv(b200flow_ctx *ctx, const double *It, const double *Ix, const double *Iy, int NC, const double2 *uv,
-                          const double2 *duv, int B, int H, int W, const PenaltySet &ps, LinSys sys) {
+                          const double2 *duv, int B, int H, int W, const PenaltySet &ps_in, LinSys sys) {
+  PenaltySet ps = ps_in;
+  BF_TRY(attach_pow_table(ctx, &ps));
   dim3 blk(32, 8), grd((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
-  BF_LAUNCH(ctx, assemble_from_deriv_kernel, grd, blk, 0, It, Ix, Iy, NC, uv, duv, H, W, ps, sys);
+  if (NC == 1 && ps.fast)
+    BF_LAUNCH(ctx, assemble_from_deriv_kernel<true>, grd, blk, 0, It, Ix, Iy, NC, uv, duv, H, W, ps, sys);
+  else
+    BF_LAUNCH(ctx, assemble_from_deriv_kernel<false>, grd, blk, 0, It, Ix, Iy, NC, uv, duv, H, W, ps, sys);
   return 0;
 }
 
