@@ -79,18 +79,20 @@ __device__ __forceinline__ double pen_weight_asm(const PenaltySet &ps, const b20
 static int attach_pow_table(b200flow_ctx *ctx, PenaltySet *ps) {
   ps->ptab = nullptr;
   ps->fast = 0;
-  if (ps->hs || !(ps->alpha < 1.0)) return 0;
+  if (ps->hs || !(ps->alpha <= 1.0)) return 0;
   const b200flow_penalty *cand[5] = {&ps->rho_d, &ps->rho_su[0], &ps->rho_su[1], &ps->rho_sv[0], &ps->rho_sv[1]};
   const b200flow_penalty *pn = nullptr;
   for (auto q : cand)
     if (q->kind == 3) { pn = q; break; }
   if (!pn || getenv("B200FLOW_POW_EXPLOG")) return 0;
-  if (!ctx->powtab) BF_CUDA(ctx, cudaMalloc(&ctx->powtab, POWTAB_DOUBLES * sizeof(double)));
-  if (ctx->powtab_a != pn->p1) {
-    BF_LAUNCH(ctx, pow_table_kernel, 1, POWTAB_BINS, 0, ctx->powtab, pn->p1 - 1.0);
-    ctx->powtab_a = pn->p1;
+  if (ps->alpha < 1.0) {            // alpha == 1 (first GNC stage): the robust penalties carry zero weight, no table is read
+    if (!ctx->powtab) BF_CUDA(ctx, cudaMalloc(&ctx->powtab, POWTAB_DOUBLES * sizeof(double)));
+    if (ctx->powtab_a != pn->p1) {
+      BF_LAUNCH(ctx, pow_table_kernel, 1, POWTAB_BINS, 0, ctx->powtab, pn->p1 - 1.0);
+      ctx->powtab_a = pn->p1;
+    }
+    ps->ptab = ctx->powtab;
   }
-  ps->ptab = ctx->powtab;
   ps->ptab_a = pn->p1;
   double c = pn->p1 - 1.0, b = 1.0;
   for (int k = 1; k <= 6; ++k) { b = b * (c - (k - 1)) / k; ps->pc[k - 1] = b; }
@@ -365,17 +367,23 @@ __device__ __forceinline__ double4 ld4(const double4 *p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// L1 prefetch (no destination register): warp_assemble is latency-bound at three CTAs per SM -- the operand streams that do
+// not depend on the flow are requested before the flow arrives, the four Hermite corners as soon as it has
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void hermite_basis(double t, double &h0, double &h1, double &g0, double &g1, double &dh0,
                                               double &dh1, double &dg0, double &dg1) {
-  double t2 = t * t, t3 = t2 * t;
-  h0 = 2.0 * t3 - 3.0 * t2 + 1.0;
-  h1 = -2.0 * t3 + 3.0 * t2;
-  g0 = t3 - 2.0 * t2 + t;
-  g1 = t3 - t2;
-  dh0 = 6.0 * t2 - 6.0 * t;
-  dh1 = -6.0 * t2 + 6.0 * t;
-  dg0 = 3.0 * t2 - 4.0 * t + 1.0;
-  dg1 = 3.0 * t2 - 2.0 * t;
+  // factored forms (14 instead of 27 fp64 instructions per axis; the library is built with -fmad=false, these are explicit):
+  // h0 = 1 - t^2 (3 - 2t), h1 = 1 - h0, g0 = t (t-1)^2, g1 = t^2 (t-1), dh0 = 6 t (t-1) = -dh1, dg0 = 1 + t (3t - 4), dg1 = t (3t - 2)
+  const double t2 = t * t, u = t - 1.0;
+  h0 = fma(t2, fma(2.0, t, -3.0), 1.0);
+  h1 = 1.0 - h0;
+  g0 = (t * u) * u;
+  g1 = t2 * u;
+  dh0 = 6.0 * (t * u);
+  dh1 = -dh0;
+  dg0 = fma(t, fma(3.0, t, -4.0), 1.0);
+  dg1 = t * fma(3.0, t, -2.0);
 }
 
 // tensor-product cubic Hermite on the unit cell == the 16x16 bcucof/bcuint product of interp2_bicubic
@@ -635,7 +643,7 @@ __device__ __forceinline__ void assemble_pixel(const PenaltySet &ps, const doubl
 // algorithmic bytes per pixel, single-channel frames: read uv 16 + im1,I1x,I1y 24 + gathered source 32,
 // write D 16 + a12 8 + WH 16 + WV 16 + rhs 16  = 144 B   (NC channels: 88 + 56 NC)
 template <bool MULTI, bool FAST>   // MULTI: NC > 1 (kept out of the single-channel instantiation: it doubles the register count)
-__global__ void __launch_bounds__(256, MULTI ? 1 : 3) warp_assemble_kernel(const double *__restrict__ frames, long long bstride, int NC,
+__global__ void __launch_bounds__(256, MULTI ? 1 : (FAST ? 4 : 3)) warp_assemble_kernel(const double *__restrict__ frames, long long bstride, int NC,
                                      const double *__restrict__ I1x,
                                      const double *__restrict__ I1y, const double4 *__restrict__ src2,
                                      const double2 *__restrict__ uv, const double2 *__restrict__ duv, int H, int W,
@@ -651,8 +659,21 @@ __global__ void __launch_bounds__(256, MULTI ? 1 : 3) warp_assemble_kernel(const
   long long i = (long long)y * W + x;
   DataTerm dt = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (in) {
+    if (!MULTI) {
+      prefetch_l1(frames + (long long)blockIdx.z * bstride + i);
+      prefetch_l1(I1x + off + i);
+      prefetch_l1(I1y + off + i);
+      if (do_assemble && y + 1 < H) prefetch_l1(uv + off + i + W);
+    }
     const double2 f = uv[off + i];
     const double2 dc = duv ? duv[off + i] : make_double2(0.0, 0.0);
+    if (!MULTI && interp == B200FLOW_INTERP_BICUBIC) {
+      const double fx = floor((double)(x + 1) + f.x), fy = floor((double)(y + 1) + f.y);
+      if (fx >= 1.0 && fx + 1.0 <= (double)W && fy >= 1.0 && fy + 1.0 <= (double)H) {
+        const double4 *t = src2 + off + (long long)((int)fy - 1) * W + ((int)fx - 1);
+        prefetch_l1(t); prefetch_l1(t + 1); prefetch_l1(t + W); prefetch_l1(t + W + 1);
+      }
+    }
     if (!MULTI) {
       Deriv dv = pixel_deriv(frames + (long long)blockIdx.z * bstride, I1x + off, I1y + off, src2 + off, H, W, x, y, f,
                              interp, blend);
