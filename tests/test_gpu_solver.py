@@ -255,3 +255,54 @@ def test_operator_as_sparse_matrix_and_custom_rhs(systems):
     x = ope._solve_linear_system(A, rhs, uv.shape)
     true_rel = float(np.linalg.norm(rhs - M @ _f(x)) / np.linalg.norm(rhs))
     assert true_rel <= 1e-10, true_rel
+
+
+@pytest.mark.parametrize("a_s,a_d,sig_s,sig_d", [(0.45, 0.45, 1e-3, 1e-3), (0.3, 0.3, 0.01, 0.5), (0.9, 0.9, 1.0, 1.0),
+                                                 (0.45, 0.25, 1e-3, 1e-3), (0.2, 0.45, 1e-3, 1e-2)])
+def test_generalized_charbonnier_weights_table_vs_oracle(a_s, a_d, sig_s, sig_d):
+    """csrc/warp.cu pow_tab: the IRLS weight 2a (sig^2 + x^2)^(a-1) (penalties.py:121-128) through the exponent / mantissa
+    table + binomial series, entry by entry against the oracle's numpy power over 30 decades of flow differences --
+    including the exp/log fallback outside 2^+-64, exponents the table was not built for (a_s != a_d: only the data
+    term's uses it) and the two-constant form of the Classic+NL-shaped sets.  Tolerance: 2e-14 RELATIVE per entry."""
+    import flow_oracle as fo
+    from optical_flow import load_of_method
+    from optical_flow.robust import RobustFunction
+    rng = np.random.default_rng(11)
+    H, W = 37, 70                                       # ragged against the 32 x 8 tiles: halo edges on every side
+    mag = 10.0 ** rng.uniform(-9, 5, size=(H, W, 2))
+    uv = mag * rng.choice([-1.0, 1.0], size=(H, W, 2))
+    uv[5, 7] = (3e12, -2e13)                            # y ~ 1e25 > 2^64: exp/log fallback
+    uv[20, 33:36, 0] = 0.25                             # exact ties: delta = 0 -> y = sig^2
+    duv = 10.0 ** rng.uniform(-6, 0, size=(H, W, 2)) * rng.choice([-1.0, 1.0], size=(H, W, 2))
+    It = 10.0 ** rng.uniform(-8, 3, size=(H, W)) * rng.choice([-1.0, 1.0], size=(H, W))
+    Ix, Iy = rng.normal(size=(H, W)) * 20, rng.normal(size=(H, W)) * 20
+    ope = load_of_method("classic+nl")
+    kind = "generalized_charbonnier"
+    ope.rho_spatial_u = [RobustFunction(kind, sig_s, a_s), RobustFunction(kind, sig_s, a_s)]
+    ope.rho_spatial_v = [RobustFunction(kind, sig_s, a_s), RobustFunction(kind, sig_s, a_s)]
+    ope.rho_data = RobustFunction(kind, sig_d, a_d)
+    A, b, _, _ = ope.flow_operator(uv, duv, It, Ix, Iy)
+    M = A.tocsr()
+    rs, rd = (kind, (sig_s, a_s)), (kind, (sig_d, a_d))
+    q = ("quadratic", (1.0,))
+    spec = dict(rho_su=[rs, rs], rho_sv=[rs, rs], rho_d=rd, qua_su=[q, q], qua_sv=[q, q], qua_d=q, lam=ope.lambda_,
+                lam_q=ope.lambda_)
+    ref = fo.assemble(uv, duv, It, Ix, Iy, spec, 0.0)
+    N = H * W
+    pix = np.arange(N).reshape(H, W, order="F")
+
+    def entries(i, j):
+        return -np.asarray(M[i.ravel(), j.ravel()]).reshape(i.shape)
+
+    worst = 0.0
+    for comp, (kh, kv) in enumerate((("wuh", "wuv"), ("wvh", "wvv"))):
+        got_h = entries(comp * N + pix[:, :-1], comp * N + pix[:, 1:])
+        got_v = entries(comp * N + pix[:-1, :], comp * N + pix[1:, :])
+        for got, want in ((got_h, ref[kh][:, :-1]), (got_v, ref[kv][:-1, :])):
+            assert np.all(want > 0)
+            worst = max(worst, float(np.max(np.abs(got - want) / want)))
+    assert worst <= 2e-14, "edge weights: worst relative error %.2e" % worst
+    a12 = np.asarray(M[pix.ravel(), N + pix.ravel()]).reshape(H, W)
+    err = float(np.max(np.abs(a12 - ref["a12"]) / np.abs(ref["a12"])))
+    assert err <= 2e-14, "data weights (through a12): worst relative error %.2e" % err
+    assert _rel(b, np.stack([ref["bu"], ref["bv"]], axis=2).reshape(-1, order="F")) < 1e-12
