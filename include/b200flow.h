@@ -119,6 +119,13 @@ int  b200flow_ctx_create(int device, b200flow_ctx **out);
 void b200flow_ctx_destroy(b200flow_ctx *ctx);
 const char *b200flow_last_error(const b200flow_ctx *ctx);   /* ctx may be NULL: last creation error */
 int  b200flow_ctx_set_timing(b200flow_ctx *ctx, int enabled);   /* per-stage CUDA-event timing into b200flow_stats */
+/* display=True of the reference's drivers ("    Iter: i j (delta: ...)" classic_nl.py:255-256, ba.py:189-190;
+ * "  Iteration: i  (norm: ...)" hs.py:123-124): with the log enabled, a single-pair run (B = 1) records one row per linear
+ * solve -- {GNC stage, pyramid level, warp, linearisation (all 0-based), ||clip(x) - duv||_2 (HS: ||x||_2)} -- in issue order.
+ * get_log copies min(cap_rows, *n_rows) rows of 5 doubles of the LAST run; the host driver prints them in the reference's
+ * format after the call returns (the whole coarse-to-fine loop is one device call, so the lines are not live). */
+int  b200flow_ctx_set_log(b200flow_ctx *ctx, int enabled);
+int  b200flow_ctx_get_log(b200flow_ctx *ctx, double *rows, int cap_rows, int *n_rows);
 /* Concurrent sub-batches (no counterpart in the reference, which is single threaded): the batched entry points cut a
  * batch of B pairs into `groups` groups that run the coarse-to-fine loop (hs.py:49-142, ba.py:57-206, classic_nl.py:89-277)
  * on their own CUDA streams, so that the HBM-bound solver of one group overlaps the issue-bound weighted median of

@@ -93,6 +93,25 @@ void b200flow_ctx_destroy(b200flow_ctx *ctx) {
 
 const char *b200flow_last_error(const b200flow_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+int b200flow_ctx_set_log(b200flow_ctx *ctx, int enabled) {
+  if (!ctx) return B200FLOW_EINVAL;
+  ctx->log_on = enabled != 0;
+  if (!ctx->log_on) ctx->log.clear();
+  return 0;
+}
+
+int b200flow_ctx_get_log(b200flow_ctx *ctx, double *rows, int cap_rows, int *n_rows) {
+  if (!ctx || !n_rows || cap_rows < 0 || (cap_rows > 0 && !rows)) return set_err(ctx, B200FLOW_EINVAL, "get_log: bad arguments");
+  const int n = (int)ctx->log.size();
+  *n_rows = n;
+  for (int k = 0; k < n && k < cap_rows; ++k) {
+    const auto &r = ctx->log[k];
+    double *o = rows + 5 * k;
+    o[0] = r.gnc; o[1] = r.level; o[2] = r.it; o[3] = r.lin; o[4] = r.v;
+  }
+  return 0;
+}
+
 int b200flow_ctx_set_timing(b200flow_ctx *ctx, int enabled) {
   if (!ctx) return B200FLOW_EINVAL;
   ctx->timing = enabled != 0;

@@ -40,6 +40,11 @@ struct b200flow_ctx {
   // resident grid sizes of the persistent solver kernels on this device (filled once by solve.cu; 0 = not yet queried)
   int grid_pcg = 0, grid_mixed = 0, grid_ic = 0;
   int ic_ctas_per_sm = 0;           // occupancy of pcg_ic_kernel as reported by the runtime
+  // display=True log of the single-pair drivers: one row per linear solve (GNC stage, pyramid level, warp, linearisation,
+  // ||clip(x) - duv||_2), filled by run_pipeline when log_on, read back through b200flow_ctx_get_log
+  struct LogRow { int gnc, level, it, lin; double v; };
+  bool log_on = false;
+  std::vector<LogRow> log;
   // table behind the generalized Charbonnier weight y^(a-1) of the assembly kernels (warp.cu, pow_table_kernel):
   // built on this context's stream whenever the exponent changes
   double *powtab = nullptr;

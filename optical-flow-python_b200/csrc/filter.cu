@@ -168,6 +168,33 @@ int k_hs_norm_gate(b200flow_ctx *ctx, const double2 *x, int B, long long n, int 
   return 0;
 }
 
+// display=True log (classic_nl.py:255-256, ba.py:189-190, hs.py:123-124): ||clip(x) - duv||_2^2 of the first pair of the batch,
+// one block, fixed order; only launched when the per-iteration log is switched on (b200flow_ctx_set_log)
+__global__ void __launch_bounds__(1024) delta_norm_kernel(const double2 *__restrict__ x, const double2 *__restrict__ sub,
+                                                           int clip, long long n, double *__restrict__ out) {
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    double2 v = x[i];
+    if (clip) { v.x = clip1(v.x); v.y = clip1(v.y); }
+    if (sub) { const double2 d = sub[i]; v.x -= d.x; v.y -= d.y; }
+    s += v.x * v.x + v.y * v.y;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += sm[w];
+    *out = t;
+  }
+}
+
+int k_delta_norm(b200flow_ctx *ctx, const double2 *x, const double2 *sub, int clip, long long n, double *out) {
+  BF_LAUNCH(ctx, delta_norm_kernel, 1, 1024, 0, x, sub, clip, n, out);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // occlusion confidence (occlusion.py:6-56)      bytes/pixel: read uv 16 + im1 8 + im2 8, write 8 = 40
 // ------------------------------------------------------------------------------------------------

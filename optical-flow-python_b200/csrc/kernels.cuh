@@ -110,6 +110,7 @@ int k_sub(b200flow_ctx *, const double2 *a, const double2 *b, double2 *out, long
 int k_weighted_median(b200flow_ctx *, const double2 *cand, const double2 *base, const double *color, int C,
                       const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out);
 int k_hs_norm_gate(b200flow_ctx *, const double2 *x, int B, long long n, int *active, double *scratch);
+int k_delta_norm(b200flow_ctx *, const double2 *x, const double2 *sub, int clip, long long n, double *out_sq);
 
 // ---- eval.cu
 int k_flow_error(b200flow_ctx *, const double2 *uv, const double2 *gt, int B, int H, int W, int border,

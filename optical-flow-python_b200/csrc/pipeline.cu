@@ -161,6 +161,8 @@ struct PipelineRun {
   StageTimer tm;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long *dstats = nullptr;
+  double *dlog = nullptr;         // display log: squared norms, one per solve (device)
+  int nlog = 0;
   int solves = 0, launches0 = 0, solver_bytes = 0;
   PipelineRun() {}
   PipelineRun(const PipelineRun &) = delete;
@@ -275,6 +277,9 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
     BF_TRY(arena_alloc(ctx, &active, (size_t)B));
     BF_TRY(arena_alloc(ctx, &nscratch, (size_t)B * 64));
   }
+  constexpr int LOG_CAP = 4096;
+  ctx->log.clear();
+  if (ctx->log_on && B == 1) BF_TRY(arena_alloc(ctx, &run->dlog, (size_t)LOG_CAP));
   if (!hs && p->max_linear > 1) {
     BF_TRY(arena_alloc(ctx, &duv, N));
     BF_TRY(arena_alloc(ctx, &It, NC * N));
@@ -360,6 +365,11 @@ static int pipeline_issue(b200flow_ctx *ctx, const b200flow_params *p, int B, in
                     mx ? 1e3 * ms / mx : 0.0, ms > 0 ? (double)sum * hw * pcg_bytes_per_pixel_iter(pcg_mode) / (ms * 1e6) : 0.0);
           }
           solves++;
+          if (run->dlog && run->nlog < LOG_CAP) {      // what the reference prints under display=True (HS: the unclipped norm)
+            BF_TRY(k_delta_norm(ctx, x, hs ? nullptr : dcur, hs ? 0 : p->limit_update, hw, run->dlog + run->nlog));
+            ctx->log.push_back({ignc, l, it, j, 0.0});
+            run->nlog++;
+          }
           const double median_bytes = 32.0 * npx, clip_bytes = 48.0 * npx;
           if (hs) {
             TIMED(B200FLOW_K_MISC, 16.0 * npx, k_hs_norm_gate(ctx, x, B, hw, active, nscratch));
@@ -426,6 +436,12 @@ static int pipeline_finish(b200flow_ctx *ctx, PipelineRun *run, bool want, cudaE
     if (ctx->band.world > 1) BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // see download() in common.cuh
     BF_CUDA(ctx, cudaMemcpyAsync(res->hstats, run->dstats, sizeof res->hstats, cudaMemcpyDeviceToHost, ctx->stream));
     BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (run->nlog > 0) {
+    std::vector<double> sq(run->nlog);
+    BF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    BF_CUDA(ctx, cudaMemcpy(sq.data(), run->dlog, sizeof(double) * run->nlog, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < run->nlog; ++k) ctx->log[k].v = sqrt(sq[k]);
   }
   if (ctx->timing) {
     if (!base) base = run->ev0;

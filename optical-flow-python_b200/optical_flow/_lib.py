@@ -104,6 +104,8 @@ _SIGS["b200flow_band_init"] = [C.c_int, C.c_int, C.c_ulonglong, C.c_int]
 _SIGS["b200flow_band_export"] = [_vp, C.POINTER(_vp)]
 _SIGS["b200flow_band_connect"] = [C.c_int, _vp, _vp]
 _SIGS["b200flow_band_close"] = []
+_SIGS["b200flow_ctx_set_log"] = [C.c_int]
+_SIGS["b200flow_ctx_get_log"] = [_vp, C.c_int, C.POINTER(C.c_int)]
 
 EXPORTS = sorted(list(_SIGS) + ["b200flow_abi_version", "b200flow_ctx_create", "b200flow_ctx_destroy",
                                 "b200flow_last_error", "b200flow_ctx_set_timing", "b200flow_ctx_sync",
@@ -187,6 +189,18 @@ class Context:
 
     def sync(self):
         self.lib.b200flow_ctx_sync(self.handle)
+
+    def set_log(self, on):
+        """display=True: record one row per linear solve of single-pair runs (include/b200flow.h, b200flow_ctx_set_log)."""
+        self.call("b200flow_ctx_set_log", int(bool(on)))
+
+    def get_log(self):
+        """Rows (gnc, level, warp, linearisation, norm) of the last single-pair run, 0-based indices."""
+        n = C.c_int(0)
+        self.call("b200flow_ctx_get_log", None, 0, C.byref(n))
+        rows = np.zeros((max(n.value, 1), 5))
+        self.call("b200flow_ctx_get_log", ptr(rows), n.value, C.byref(n))
+        return rows[:n.value]
 
     def set_split(self, groups, solver_ctas_per_sm=0):
         """Concurrent sub-batches: batched calls run `groups` groups of pairs on their own streams (include/b200flow.h)."""

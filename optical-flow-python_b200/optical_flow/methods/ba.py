@@ -42,14 +42,19 @@ class BAOpticalFlow(BaseOpticalFlow):
         untouched, as the reference restores it."""
         self._check_fc()
         images = _lib.f64(self.images)
-        t0 = time.time()
+        t0 = self._display_t0 = time.time()
+        self._stage_lines = 0
         P = self._c_params(levels=self._levels(images))
         if self.pyramid_levels < 1:
             P.pyramid_levels, P.auto_level = 0, 1
         self._apply_solver(P)
-        uv = self._run(P, images, None, init)
-        if self.display:
-            print(f"{self.gnc_iters} GNC stages finished, {(time.time() - t0) / 60:.2f} minutes passed")
+        uv = self._run(P, images, None, init, log_style='gnc')
+        # ba.py:132-133: one "finished" line per stage, display or not (with display on, the earlier stages' lines were
+        # already printed between the log lines)
+        for k in range(self._stage_lines, int(self.gnc_iters) - 1):
+            self._print_stage_done(k)
+        if int(self.gnc_iters) >= 1:
+            print(f"GNC stage {int(self.gnc_iters)} finished, {(time.time() - t0) / 60:.2f} minutes passed")
         return uv
 
     def compute_flow_base(self, uv):
@@ -58,7 +63,7 @@ class BAOpticalFlow(BaseOpticalFlow):
         P.texture = -1
         P.gnc_iters = 1
         self._apply_solver(P)
-        return self._run(P, self.images, None, uv)
+        return self._run(P, self.images, None, uv, log_style='gnc_base')
 
     def flow_operator(self, uv, duv, It, Ix, Iy):
         """(A, b, None, iterative) for this object's own penalties and lambda_ (ba.py:208-302); A is matrix-free."""

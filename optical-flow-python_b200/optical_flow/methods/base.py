@@ -302,8 +302,10 @@ class BaseOpticalFlow(ABC):
         if self.fc and not self.texture:
             raise NotImplementedError("fc=True (Gaussian high-pass preprocessing) is not built; no preset uses it")
 
-    def _run(self, P, images, color, init):
-        """One b200flow_estimate call for a single pair."""
+    def _run(self, P, images, color, init, log_style=None):
+        """One b200flow_estimate call for a single pair.  log_style ('gnc', 'hs', or their single-level forms 'gnc_base',
+        'hs_base') + self.display: the reference's per-level / per-iteration display lines, printed from the device log
+        after the call (the whole loop is one device call)."""
         images = _lib.f64(images)
         if images.ndim != 3 or images.shape[2] < 2 or images.shape[2] % 2:
             raise ValueError("images must be (H, W, 2C): C channels of frame 1 followed by C channels of frame 2")
@@ -323,10 +325,58 @@ class BaseOpticalFlow(ABC):
         uv = np.empty((H, W, 2))
         st = _lib.Stats()
         ctx = _lib.default_context()
-        ctx.call("b200flow_estimate_mc", P, 1, H, W, nc, Cn, _lib.ptr(images), _lib.ptr(color), _lib.ptr(init),
-                 _lib.ptr(uv), _lib.C.byref(st))
+        show = bool(self.display) and log_style is not None
+        if show:
+            ctx.set_log(True)
+        try:
+            ctx.call("b200flow_estimate_mc", P, 1, H, W, nc, Cn, _lib.ptr(images), _lib.ptr(color), _lib.ptr(init),
+                     _lib.ptr(uv), _lib.C.byref(st))
+            if show:
+                self._print_display_log(ctx.get_log(), log_style)
+        finally:
+            if show:
+                ctx.set_log(False)
         self.last_stats = st.as_dict()
         return uv
+
+    _display_t0 = None     # set by compute_flow: start of the run, for the "minutes passed" lines
+    _stage_lines = 0       # "GNC stage k finished" lines printed so far in this run
+
+    def _print_display_log(self, rows, style):
+        """The lines the reference prints under display=True, in its order and format: classic_nl.py:141-152,255-256,
+        186-198; ba.py:100-114,189-190,132-133; hs.py:80-81,123-124 (HS stops a level at the first ||x|| < 1e-3, hs.py:126)."""
+        import time
+        hs = style.startswith('hs')
+        full = not style.endswith('_base')
+        last_g = last_l = None
+        gated = False
+        for g, l, i, j, v in rows:
+            g, l, i, j = int(g), int(l), int(i), int(j)
+            if full and not hs and g != last_g:
+                if last_g is not None:
+                    self._print_stage_done(last_g)
+                print(f"GNC stage: {g + 1}")
+                last_l = None
+            if (g, l) != (last_g, last_l):
+                gated = False
+                if full:
+                    print(f"Pyramid level: {l + 1}" if hs else f"  Pyramid level: {l + 1}")
+            last_g, last_l = g, l
+            if hs:
+                if gated:
+                    continue
+                print(f"  Iteration: {i + 1}  (norm: {v:.6f})")
+                gated = v < 1e-3
+            else:
+                print(f"    Iter: {i + 1} {j + 1} (delta: {v:.6f})")
+        if full and not hs and last_g is not None and last_g + 1 < int(self.gnc_iters):
+            self._print_stage_done(last_g)     # the last stage's line is the caller's (it may carry AAE / EPE)
+
+    def _print_stage_done(self, g):
+        import time
+        t0 = self._display_t0 or time.time()
+        self._stage_lines = g + 1
+        print(f"GNC stage {g + 1} finished, {(time.time() - t0) / 60:.2f} minutes passed")
 
     # ---- reference-compatible helpers ---------------------------------------------------------------
     def _solve_linear_system(self, A, b, uv_shape, x0=None):

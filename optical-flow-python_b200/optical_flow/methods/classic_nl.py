@@ -58,23 +58,28 @@ class ClassicNLOpticalFlow(BaseOpticalFlow):
         GNC alpha reached at the end is kept on the object (it is NOT restored, classic_nl.py:181-184)."""
         self._check_fc()
         images = _lib.f64(self.images)
-        t0 = time.time()
+        t0 = self._display_t0 = time.time()
+        self._stage_lines = 0
         if self.auto_level:
             self.pyramid_levels = self._auto_pyramid_levels(images)
         P = self._c_params(levels=self.pyramid_levels)
         if self.pyramid_levels < 1:
             P.pyramid_levels, P.auto_level = 0, 1
         self._apply_solver(P)
-        uv = self._run(P, images, self._color_for(images.shape[:2]), init)
+        uv = self._run(P, images, self._color_for(images.shape[:2]), init, log_style='gnc')
         for ignc in range(int(self.gnc_iters)):
             if self.gnc_iters > 1:
                 self.alpha = max(0, min(self.alpha, 1 - (ignc + 1) / (self.gnc_iters - 1)))
+        # the reference prints one such line after EVERY stage, display or not (classic_nl.py:186-198); with display on the
+        # earlier stages' lines come interleaved from the device log (_print_display_log)
+        for k in range(self._stage_lines, int(self.gnc_iters) - 1):
+            self._print_stage_done(k)
         msg = f"GNC stage {int(self.gnc_iters)} finished, {(time.time() - t0) / 60:.2f} minutes passed"
         if gt is not None:
             from optical_flow.evaluation.metrics import flow_angular_error
             aae, stdae, aepe = flow_angular_error(gt[:, :, 0], gt[:, :, 1], uv[:, :, 0], uv[:, :, 1], 0)
             msg += f"  AAE {aae:.3f} STD {stdae:.3f} EPE {aepe:.3f}"
-        if self.display or gt is not None:
+        if int(self.gnc_iters) >= 1:
             print(msg)
         return uv
 
@@ -84,7 +89,7 @@ class ClassicNLOpticalFlow(BaseOpticalFlow):
         P.texture = -1
         P.gnc_iters = 1
         self._apply_solver(P)
-        return self._run(P, self.images, self._color_for(np.shape(self.images)[:2]), uv)
+        return self._run(P, self.images, self._color_for(np.shape(self.images)[:2]), uv, log_style='gnc_base')
 
     def flow_operator(self, uv, duv, It, Ix, Iy):
         return self._gnc_flow_operator(uv, duv, It, Ix, Iy)

@@ -39,7 +39,7 @@ class HSOpticalFlow(BaseOpticalFlow):
         if self.pyramid_levels < 1:
             P.pyramid_levels, P.auto_level = 0, 1     # min(H, W) < 16: no level runs, flow = init (+ final median)
         self._apply_solver(P)
-        return self._run(P, images, None, init)
+        return self._run(P, images, None, init, log_style='hs')
 
     def _copy_with_images(self, images):
         small = self._level_copy()
@@ -53,7 +53,7 @@ class HSOpticalFlow(BaseOpticalFlow):
         P.texture = -1
         P.final_median = 0
         self._apply_solver(P)
-        return self._run(P, self.images, None, uv)
+        return self._run(P, self.images, None, uv, log_style='hs_base')
 
     def flow_operator(self, uv, duv=None, It=None, Ix=None, Iy=None):
         """(A, b, None, True) with A matrix-free (hs.py:144-203); derivatives are recomputed from uv as in the reference."""
