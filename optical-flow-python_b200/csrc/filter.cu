@@ -349,21 +349,9 @@ __device__ __forceinline__ unsigned wm_pack(double w, double scale) {
 template <int NPL, int NFULL>
 __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const double (&w)[NPL],
                                                   const unsigned (&pk)[NPL], int n, double half, double2 *scratch,
-                                                  int lane) {
-  // value range in fp32 with outward rounding (FMNMX instead of fp64 compare + select pairs)
-  // (slots k < NFULL hold a real sample in every lane: no +inf padding to filter out of the maximum there)
-  float flo = __double2float_rd(x[0]), fhi = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < NPL; ++k) {
-    flo = fminf(flo, __double2float_rd(x[k]));
-    const float u = __double2float_ru(x[k]);
-    fhi = fmaxf(fhi, (k >= NFULL && u == INFINITY) ? -INFINITY : u);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    flo = fminf(flo, __shfl_xor_sync(0xffffffffu, flo, o));
-    fhi = fmaxf(fhi, __shfl_xor_sync(0xffffffffu, fhi, o));
-  }
+                                                  int lane, float flo, float fhi) {
+  // [flo, fhi]: fp32 outer bounds of the window's values (window_ranges: a separable min / max over the staged tile, ~10
+  // warp instructions per pixel instead of a 55-instruction reduction over the registers per selection)
   double L = next_below((double)flo), R = (double)fhi;   // open-closed value bracket: S(L) = 0 < half <= S(R) = total
   int nL = 0, nR = n;                                    // samples <= L, <= R
   unsigned FL = 0u;                                      // fixed-point lower bound of S(L): S(L) * 2^22 / total in [FL, FL + nL]
@@ -469,6 +457,42 @@ __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const 
   return ans;
 }
 
+// Value range of every output pixel's window, for both flow components: separable min / max over the staged tile in fp32
+// (values rounded to nearest on staging, the result widened by one fp32 ulp on each side, so [lo, hi] always contains the
+// window).  s_f: [SH][SW] staged {u, v}; s_rr: [SH][WM_TW] row pass; s_rng: [WM_TH][WM_TW] {ulo, uhi, vlo, vhi}.
+// Called by all threads of the CTA; the caller synchronises before s_f is read and after s_rng is written.
+__device__ __forceinline__ float f32_below(float v) {
+  const int b = __float_as_int(v);
+  return v > 0.f ? __int_as_float(b - 1) : (v < 0.f ? __int_as_float(b + 1) : -1.4e-45f);
+}
+__device__ __forceinline__ float f32_above(float v) {
+  const int b = __float_as_int(v);
+  return v > 0.f ? __int_as_float(b + 1) : (v < 0.f ? __int_as_float(b - 1) : 1.4e-45f);
+}
+__device__ __forceinline__ void window_ranges(const float2 *s_f, float4 *s_rr, float4 *s_rng, int SW, int SH, int wsz,
+                                              int TW, int TH) {
+  for (int t = threadIdx.x; t < SH * TW; t += blockDim.x) {
+    const int sy = t / TW, lx = t - sy * TW;
+    const float2 *row = s_f + sy * SW + lx;
+    float2 e = row[0];
+    float ulo = e.x, uhi = e.x, vlo = e.y, vhi = e.y;
+    for (int dx = 1; dx < wsz; ++dx) {
+      e = row[dx];
+      ulo = fminf(ulo, e.x); uhi = fmaxf(uhi, e.x); vlo = fminf(vlo, e.y); vhi = fmaxf(vhi, e.y);
+    }
+    s_rr[t] = make_float4(ulo, uhi, vlo, vhi);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < TH * TW; t += blockDim.x) {
+    float4 r = s_rr[t];
+    for (int dy = 1; dy < wsz; ++dy) {
+      const float4 q = s_rr[t + dy * TW];
+      r.x = fminf(r.x, q.x); r.y = fmaxf(r.y, q.y); r.z = fminf(r.z, q.z); r.w = fmaxf(r.w, q.w);
+    }
+    s_rng[t] = make_float4(f32_below(r.x), f32_above(r.y), f32_below(r.z), f32_above(r.w));
+  }
+}
+
 #ifndef WM_MINB
 #define WM_MINB 3                // CTAs per SM the register budget is cut for: 3 (80 registers) 106 ms of filter time per bench step, 2 (128) 116 ms, 4 (64) 126 ms
 #endif
@@ -488,6 +512,9 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
   double2 *s_uv = reinterpret_cast<double2 *>(smem);                      // [SN]
   double4 *s_cw = reinterpret_cast<double4 *>(smem + 2 * SN);             // [SN]
   double2 *s_scr = reinterpret_cast<double2 *>(smem + 6 * SN) + 32 * (threadIdx.x >> 5);   // [WM_WARPS][32] compaction scratch
+  float2 *s_f = reinterpret_cast<float2 *>(reinterpret_cast<double2 *>(smem + 6 * SN) + 32 * WM_WARPS);   // [SN] fp32 copy of the flow
+  float4 *s_rr = reinterpret_cast<float4 *>(s_f + SN);                    // [SH][WM_TW] row pass of window_ranges
+  float4 *s_rng = s_rr + SH * WM_TW;                                      // [WM_TH][WM_TW] value ranges
   const int b = blockIdx.z;
   const long long HW = (long long)H * W, off = (long long)b * HW;
   const int x0 = blockIdx.x * WM_TW, y0 = blockIdx.y * WM_TH;
@@ -497,6 +524,7 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
     long long gi = (long long)gy * W + gx;
     double2 f = cand[off + gi];
     s_uv[t] = make_double2(f.x + 0.0, f.y + 0.0);              // canonicalise -0.0
+    s_f[t] = make_float2(__double2float_rn(f.x), __double2float_rn(f.y));
     const double *cp = color + (long long)b * C * HW + gi;
     s_cw[t] = make_double4(cp[0], C > 1 ? cp[HW] : 0.0, C > 2 ? cp[2 * HW] : 0.0, occ[off + gi]);
   }
@@ -513,6 +541,8 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
     vmask |= e < n ? 1u << k : 0u;
   }
   __syncthreads();
+  window_ranges(s_f, s_rr, s_rng, SW, SH, wsz, WM_TW, WM_TH);
+  __syncthreads();
   const int py = y0 + warp;
   if (py >= H) return;
   for (int lx = 0; lx < WM_TW; ++lx) {
@@ -520,6 +550,7 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
     if (px >= W) break;
     const int org = warp * SW + lx;
     const double4 cc = s_cw[org + hsz * SW + hsz];
+    const float4 rng = s_rng[warp * WM_TW + lx];
     double x[NPL], w[NPL];
     double tot = 0.0;
 #pragma unroll
@@ -547,10 +578,10 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
     // padding slots: x = +inf with zero weight (never counted, weighed or bracketed)
 #pragma unroll
     for (int k = 0; k < NPL; ++k) x[k] = (k < NFULL || ((vmask >> k) & 1u)) ? s_uv[org + qoff[k]].x : INFINITY;
-    const double mu = weighted_select<NPL, NFULL>(x, w, pk, n, half, s_scr, lane);
+    const double mu = weighted_select<NPL, NFULL>(x, w, pk, n, half, s_scr, lane, rng.x, rng.y);
 #pragma unroll
     for (int k = 0; k < NPL; ++k) x[k] = (k < NFULL || ((vmask >> k) & 1u)) ? s_uv[org + qoff[k]].y : INFINITY;
-    const double mv = weighted_select<NPL, NFULL>(x, w, pk, n, half, s_scr, lane);
+    const double mv = weighted_select<NPL, NFULL>(x, w, pk, n, half, s_scr, lane, rng.z, rng.w);
     if (lane == 0) {
       long long gi = off + (long long)py * W + px;
       if (base) {
@@ -567,7 +598,8 @@ template <int NPL, int NFULL>
 static int launch_wmedian(b200flow_ctx *ctx, const double2 *cand, const double2 *base, const double *color, int C,
                           const double *occ, int B, int H, int W, int hsz, double sigma_i, double2 *out) {
   int SW = WM_TW + 2 * hsz, SH = WM_TH + 2 * hsz;
-  size_t smem = (size_t)SW * SH * 6 * sizeof(double) + WM_WARPS * 32 * sizeof(double2);
+  size_t smem = (size_t)SW * SH * 6 * sizeof(double) + WM_WARPS * 32 * sizeof(double2)          // staged tile + compaction scratch
+                + (size_t)SW * SH * sizeof(float2) + (size_t)(SH + WM_TH) * WM_TW * sizeof(float4);   // window_ranges: fp32 flow, row pass, ranges
   if (smem > 200 * 1024) return set_err(ctx, B200FLOW_EINVAL, "weighted median window hsz=%d needs %zu B of shared memory", hsz, smem);
   {
     // function attributes once per process, device and window size (mutex-guarded): setting an attribute of a kernel that is
