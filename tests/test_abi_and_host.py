@@ -208,3 +208,27 @@ def test_pinned_result_buffers_are_recycled_only_when_released():
         assert f.n == 3 and e.shape == (4, 5, 2) and e.flags["OWNDATA"] and not d.flags["OWNDATA"]
     finally:
         _lib.PINNED_CAP_BYTES = old_cap
+
+
+def test_display_log_is_printed_in_the_reference_format(capsys):
+    """Host side of display=True (methods/base.py _print_display_log): rows {stage, level, warp, linearisation, norm} from the
+    device log become the reference's lines (classic_nl.py:141-152,255-256,186-198; hs.py:80-81,123-127) -- no GPU needed."""
+    from optical_flow import load_of_method
+    ope = load_of_method("classic+nl-fast")
+    ope._stage_lines = 0
+    rows = np.array([[0, 1, 0, 0, 8.5], [0, 1, 1, 0, 3.25], [0, 0, 0, 0, 12.0], [1, 0, 0, 0, 1.0], [1, 0, 0, 1, 0.5]])
+    ope._print_display_log(rows, "gnc")
+    out = capsys.readouterr().out.splitlines()
+    assert out[:6] == ["GNC stage: 1", "  Pyramid level: 2", "    Iter: 1 1 (delta: 8.500000)", "    Iter: 2 1 (delta: 3.250000)",
+                       "  Pyramid level: 1", "    Iter: 1 1 (delta: 12.000000)"]
+    assert out[6].startswith("GNC stage 1 finished, ") and out[6].endswith(" minutes passed")
+    assert out[7:] == ["GNC stage: 2", "  Pyramid level: 1", "    Iter: 1 1 (delta: 1.000000)", "    Iter: 1 2 (delta: 0.500000)"]
+    assert ope._stage_lines == 1                    # the last stage's "finished" line is compute_flow's (it may carry AAE / EPE)
+    ope._print_display_log(rows[:2], "gnc_base")   # compute_flow_base prints the iteration lines only
+    assert capsys.readouterr().out.splitlines() == ["    Iter: 1 1 (delta: 8.500000)", "    Iter: 2 1 (delta: 3.250000)"]
+    hs = load_of_method("hs")
+    hs._print_display_log(np.array([[0, 1, 0, 0, 1.0], [0, 1, 1, 0, 5e-4], [0, 1, 2, 0, 0.3], [0, 0, 0, 0, 2.0]]), "hs")
+    # Horn-Schunck leaves a level at the first ||x|| < 1e-3 (hs.py:126-127): later solves of that level are not printed
+    assert capsys.readouterr().out.splitlines() == ["Pyramid level: 2", "  Iteration: 1  (norm: 1.000000)",
+                                                    "  Iteration: 2  (norm: 0.000500)", "Pyramid level: 1",
+                                                    "  Iteration: 1  (norm: 2.000000)"]
