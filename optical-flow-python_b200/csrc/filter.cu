@@ -289,6 +289,7 @@ __device__ __forceinline__ double wmax(double v) {
 __constant__ double WM_EXPC[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
                                    1.0 / 362880.0,     1.0 / 40320.0,     1.0 / 5040.0,     1.0 / 720.0,
                                    1.0 / 120.0,        1.0 / 24.0,        1.0 / 6.0,        0.5};
+__constant__ double WM_FLOOR = 1e-10;      // np.maximum(w, 1e-10): a constant-bank operand (an fp64 literal costs two moves per use)
 __device__ __forceinline__ double exp_nonpos(double a) {
   const double t = fma(a, 1.4426950408889634, 6755399441055744.0);
   const int k = max(__double2loint(t), -1000);                // a < -693: any value below the 1e-10 floor will do
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(WM_WARPS * 32, WM_MINB) wmedian_kernel(const d
       cd += d2 * d2;
       const double wk = exp_nonpos(-cd * inv2s2) * cq.w;
       // np.maximum(w, 1e-10); padding slots get weight 0
-      const double wfl = fmax(wk, 1e-10);
+      const double wfl = wk > WM_FLOOR ? wk : WM_FLOOR;
       w[k] = (k < NFULL || ((vmask >> k) & 1u)) ? wfl : 0.0;
       tot += w[k];
     }
