@@ -351,9 +351,10 @@ template <int NPL, int NFULL>
 __device__ __forceinline__ double weighted_select(const double (&x)[NPL], const double (&w)[NPL],
                                                   const unsigned (&pk)[NPL], int n, double half, double2 *scratch,
                                                   int lane, float flo, float fhi) {
-  // [flo, fhi]: fp32 outer bounds of the window's values (window_ranges: a separable min / max over the staged tile, ~10
-  // warp instructions per pixel instead of a 55-instruction reduction over the registers per selection)
-  double L = next_below((double)flo), R = (double)fhi;   // open-closed value bracket: S(L) = 0 < half <= S(R) = total
+  // flo < every sample <= fhi: fp32 STRICT lower / upper bounds of the window's values (window_ranges: a separable min / max
+  // over the staged tile widened by one fp32 ulp, ~10 warp instructions per pixel instead of a 55-instruction reduction over
+  // the registers per selection)
+  double L = (double)flo, R = (double)fhi;               // open-closed value bracket: S(L) = 0 < half <= S(R) = total
   int nL = 0, nR = n;                                    // samples <= L, <= R
   unsigned FL = 0u;                                      // fixed-point lower bound of S(L): S(L) * 2^22 / total in [FL, FL + nL]
   while (nR - nL > 32) {
