@@ -132,6 +132,30 @@ def test_batch_equals_single(stages):
     assert_close(uv[0], g["uv"], E2E_TOL, "batch item 0 vs reference")
 
 
+@pytest.mark.parametrize("method", ["classic+nl-fast", "hs-brightness", "ba-brightness"])
+def test_batch_of_float_and_gray_inputs_equals_single(stages, method):
+    """estimate_flow_batch beyond uint8 RGB: float RGB stacks, gray (B, H, W) stacks and two-channel float stacks are prepared
+    pair by pair as estimate_flow prepares them (interface.py:40-66) and solved as one batch (b200flow_estimate_mc, B > 1)."""
+    from optical_flow import estimate_flow, estimate_flow_batch
+    a, b = stages["rgb1"].astype(float), stages["rgb2"].astype(float)
+    params = {"max_iters": 2} if method.startswith("ba") else None
+    cases = {
+        "float rgb": (np.stack([a, b]) + 0.25, np.stack([b, a]) + 0.25),
+        "gray": (np.stack([stages["gray1"], stages["gray2"]]), np.stack([stages["gray2"], stages["gray1"]])),
+        "two channels": (np.stack([a[:, :, :2], b[:, :, :2]]), np.stack([b[:, :, :2], a[:, :, :2]])),
+        "uint8 gray": (np.stack([stages["gray1"], stages["gray2"]]).astype(np.uint8),
+                       np.stack([stages["gray2"], stages["gray1"]]).astype(np.uint8)),
+    }
+    for name, (i1, i2) in cases.items():
+        uv, st = estimate_flow_batch(i1, i2, method, params, return_stats=True)
+        assert uv.shape == i1.shape[:3] + (2,) and st["not_converged"] == 0
+        for k in range(len(i1)):
+            single = estimate_flow(i1[k], i2[k], method, params)
+            assert_close(uv[k], single, 1e-6, "%s, %s: batch item %d vs single" % (method, name, k))
+    with pytest.raises(ValueError):
+        estimate_flow_batch(np.zeros((2, 8, 8, 3)), np.zeros((2, 8, 9, 3)), method)
+
+
 def test_tiny_image_quirk():
     """min(H, W) < 16 -> auto pyramid levels <= 0: GNC stage 0 runs no level; Horn-Schunck then only
     applies its final median to init, BA still runs its gnc_pyramid_levels in stages 1.. (ba.py:104-110)."""
