@@ -227,7 +227,11 @@ def workload_config(B, solver_precision="mixed", tol=1e-10):
     return {"workload": "classic+nl-fast, synthetic 640x480 RGB pairs (affine flow, seeds 3..), fp64, "
                         "%d pairs per GPU per step" % B,
             "method": METHOD, "height": H, "width": W, "pairs_per_gpu_per_step": B,
-            "parallelism": "independent frame pairs per GPU, no collective"}
+            "parallelism": "independent frame pairs per GPU, no collective",
+            # timing rule: flush L2 between timed iterations OR use inputs larger than L2 -- the latter holds by construction
+            "l2": "no flush needed: one step streams ~%.1f GB of fp64 working set (pyramids, 72 B/pixel linear systems, 64 B/pixel "
+                  "Krylov vectors for %d pairs) and ~650 GB of traffic through the 126 MB L2 between two reads of the same input"
+                  % (B * H * W * 650e-9, B)}
 
 
 def run_reference_arm(args, rank, world):
